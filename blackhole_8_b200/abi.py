@@ -1,0 +1,160 @@
+"""ctypes mirror of include/bh8.h (the C ABI of the B200 geodesic renderer).
+
+Field order and types must stay in lock-step with the header; tests/test_abi.py checks the struct
+sizes against the values the compiled library reports.
+"""
+import ctypes as C
+import json
+
+import numpy as np
+
+ABI_VERSION = 1
+MAX_OBJECTS = 16
+MAX_TEXTURES = 16
+
+KIND_BLACKHOLE, KIND_ANNULUS, KIND_RECTANGLE, KIND_INFINITE_PLANE = 0, 1, 2, 3
+CLASS_BACKGROUND, CLASS_HORIZON, CLASS_DISC, CLASS_OBJECT = 0, 1, 2, 3
+PATTERN_BLACK, PATTERN_CHESS = 0, 1
+PIXEL_RGBA8, PIXEL_BGRA8, PIXEL_BGR8 = 0, 1, 2
+FLAG_STATS, FLAG_NO_COMPACTION = 1, 2
+
+EINVAL, EUNSUPPORTED, ECUDA, ENOMEM, ENODEVICE = -1, -2, -3, -4, -5
+
+Vec3 = C.c_double * 3
+
+
+class Camera(C.Structure):
+    _fields_ = [
+        ("pos", Vec3),
+        ("vx", Vec3),
+        ("vy", Vec3),
+        ("vz", Vec3),
+        ("focus_len", C.c_double),
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+    ]
+
+
+class Object(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32),
+        ("key", C.c_int32),
+        ("tex_id", C.c_int32),
+        ("pattern", C.c_int32),
+        ("v", Vec3 * 5),
+        ("n", Vec3),
+        ("ex", Vec3),
+        ("ey", Vec3),
+        ("r_in", C.c_double),
+        ("r_out", C.c_double),
+        ("mass", C.c_double),
+        ("pattern_size", C.c_double),
+    ]
+
+
+class Scene(C.Structure):
+    _fields_ = [
+        ("n_obj", C.c_int32),
+        ("bh_index", C.c_int32),
+        ("obj", C.POINTER(Object)),
+    ]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("nstep", C.c_int32),
+        ("pixel_format", C.c_int32),
+        ("flags", C.c_uint32),
+        ("stripe_rows", C.c_int32),
+        ("shard_index", C.c_int32),
+        ("shard_count", C.c_int32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("rays", C.c_uint64),
+        ("steps", C.c_uint64),
+        ("class_count", C.c_uint64 * 4),
+        ("tex_oob", C.c_uint64),
+        ("kernel_ms", C.c_double),
+        ("total_ms", C.c_double),
+    ]
+
+
+def pixel_bytes(pixel_format):
+    return 3 if pixel_format == PIXEL_BGR8 else 4
+
+
+class SceneSnapshot:
+    """A scene + camera snapshot held as ctypes PODs (what bh8_render consumes).
+
+    Built from the JSON that oracle/_ref/ref_render (reference classes) or the repo's own C++
+    snapshot helper writes; `textures` lists the reference resource names by texture slot.
+    """
+
+    def __init__(self, camera, objects, bh_index, textures=(), nstep=20, meta=None):
+        self.camera = camera
+        self.objects = (Object * len(objects))(*objects)
+        self.scene = Scene(len(objects), bh_index, C.cast(self.objects, C.POINTER(Object)))
+        self.textures = list(textures)
+        self.nstep = nstep
+        self.meta = meta or {}
+
+    @property
+    def width(self):
+        return self.camera.width
+
+    @property
+    def height(self):
+        return self.camera.height
+
+    @classmethod
+    def from_dict(cls, d):
+        c = d["camera"]
+        cam = Camera(Vec3(*c["pos"]), Vec3(*c["vx"]), Vec3(*c["vy"]), Vec3(*c["vz"]),
+                     c["focus_len"], c["width"], c["height"])
+        objs = []
+        for o in d["objects"]:
+            v = o["v"]
+            rows = (Vec3 * 5)(*[Vec3(*v[3 * i:3 * i + 3]) for i in range(5)])
+            objs.append(Object(o["kind"], o["key"], o["tex_id"], o["pattern"], rows, Vec3(*o["n"]),
+                               Vec3(*o["ex"]), Vec3(*o["ey"]), o["r_in"], o["r_out"], o["mass"],
+                               o["pattern_size"]))
+        meta = {k: d[k] for k in ("cfg", "frame", "run") if k in d}
+        return cls(cam, objs, d["bh_index"], d.get("textures", ()), d.get("nstep", 20), meta)
+
+    @classmethod
+    def from_json(cls, path):
+        with open(path) as f:
+            return cls.from_dict(json.load(f))
+
+    def to_dict(self):
+        c = self.camera
+        objs = []
+        for o in self.objects:
+            objs.append({
+                "kind": o.kind, "key": o.key, "tex_id": o.tex_id, "pattern": o.pattern,
+                "v": [x for row in o.v for x in row], "n": list(o.n), "ex": list(o.ex),
+                "ey": list(o.ey), "r_in": o.r_in, "r_out": o.r_out, "mass": o.mass,
+                "pattern_size": o.pattern_size,
+            })
+        return {
+            "nstep": self.nstep, "width": c.width, "height": c.height,
+            "camera": {"pos": list(c.pos), "vx": list(c.vx), "vy": list(c.vy), "vz": list(c.vz),
+                       "focus_len": c.focus_len, "width": c.width, "height": c.height},
+            "textures": list(self.textures), "bh_index": self.scene.bh_index, "objects": objs,
+        }
+
+    def with_resolution(self, width, height, fov=None):
+        """Same scene seen by Camera(width, height, fov): focus_len = width/(2 tan(fov/2)),
+        camera.h:37-41.  The reference picture depends on the resolution, so this is a different
+        workload, not a resampling."""
+        d = self.to_dict()
+        old = d["camera"]
+        if fov is None:
+            fov = 2.0 * np.arctan(old["width"] / (2.0 * old["focus_len"]))
+        d["camera"]["focus_len"] = float(width / (2.0 * np.tan(fov / 2.0)))
+        d["camera"]["width"] = d["width"] = int(width)
+        d["camera"]["height"] = d["height"] = int(height)
+        return SceneSnapshot.from_dict(d)

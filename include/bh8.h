@@ -1,0 +1,196 @@
+/* bh8.h -- C ABI of the B200 renderer for blackhole_8's per-pixel null-geodesic hot path.
+ *
+ * The reference (lackhole/blackhole_8) has NO plugin / operator / FFI seam for this path: the
+ * pixel loop is written inline in main() of include/blackhole/blackhole_solution_test.cc:161-308
+ * and calls per-pixel C++ member functions.  This header is therefore the boundary a maintainer
+ * would add: one batched call "scene snapshot + camera(s) -> frame(s)" that replaces the whole
+ * loop body, with plain-old-data mirrors of the state that loop reads:
+ *
+ *   bh8_camera   <- blackhole::Camera<double>          camera.h:30-63  (position, basis, focus_len)
+ *   bh8_object   <- blackhole::DrawableObject<double>  object/object.h:33-109 (vertex()[0..4]) plus
+ *                   StaticBlackhole  blackhole_solution.h:24-88   (mass)
+ *                   Annulus          object/vector_object.h:320-355 (norm_, r_outer_, r_inner_)
+ *                   Rectangle        object/vector_object.h:94-179
+ *                   InfinitePlane    object/vector_object.h:203-232 (position, vector_x/y/z) with
+ *                   ChessPattern2D   object/pattern.h:20-47       (pattern_size_)
+ *   bh8_scene    <- blackhole::ObjectManager<double>   object/object_manager.h:69-92 (objects_)
+ *   textures     <- Material::texture_ (cv::Mat CV_8UC3, BGR)  object/material.h:29-60
+ *   output       <- the cv::Mat frame written at blackhole_solution_test.cc:214,231-233
+ *
+ * Plain pointers and sizes only; the caller owns every host buffer, the context owns all device
+ * memory, streams and texture objects.  Every function returns 0 on success and a negative
+ * BH8_E* code on failure; bh8_last_error() gives the message.  There is no CPU fallback: without a
+ * usable CUDA device bh8_create() fails.
+ */
+#ifndef BH8_H_
+#define BH8_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BH8_ABI_VERSION 1
+#define BH8_MAX_OBJECTS 16
+#define BH8_MAX_TEXTURES 16
+#define BH8_MAX_DEVICES 8
+
+/* error codes */
+#define BH8_OK 0
+#define BH8_EINVAL (-1)      /* bad argument / malformed scene */
+#define BH8_EUNSUPPORTED (-2) /* object kind or pattern the GPU path does not implement */
+#define BH8_ECUDA (-3)       /* CUDA runtime error (message has the cudaError string) */
+#define BH8_ENOMEM (-4)
+#define BH8_ENODEVICE (-5)   /* no CUDA device: there is no CPU fallback */
+
+/* object kinds (which Collide()/color() pair of the reference applies) */
+enum {
+  BH8_KIND_BLACKHOLE = 0,      /* StaticBlackhole: horizon sphere R = 2M, colour black */
+  BH8_KIND_ANNULUS = 1,        /* thin accretion disc */
+  BH8_KIND_RECTANGLE = 2,      /* textured rectangle */
+  BH8_KIND_INFINITE_PLANE = 3  /* plane with a procedural pattern */
+};
+
+/* per-pixel hit class written to the optional class map */
+enum {
+  BH8_CLASS_BACKGROUND = 0, /* FindCollision returned nullptr on every segment: pixel stays 0 */
+  BH8_CLASS_HORIZON = 1,
+  BH8_CLASS_DISC = 2,
+  BH8_CLASS_OBJECT = 3
+};
+
+/* InfinitePlane pattern_ (an opaque std::function in the reference; only these are recognised) */
+enum {
+  BH8_PATTERN_BLACK = 0, /* the default lambda: always (0,0,0) */
+  BH8_PATTERN_CHESS = 1  /* ChessPattern2D{pattern_size} */
+};
+
+/* pixel formats of the output frame */
+enum {
+  BH8_PIXEL_RGBA8 = 0, /* 4 B/pixel R,G,B,255 */
+  BH8_PIXEL_BGRA8 = 1, /* 4 B/pixel B,G,R,255 */
+  BH8_PIXEL_BGR8 = 2   /* 3 B/pixel B,G,R: the reference's CV_8UC3 cv::Mat layout */
+};
+
+/* bh8_params.flags */
+#define BH8_FLAG_STATS 1u        /* accumulate bh8_stats counters on the device (tiny cost) */
+#define BH8_FLAG_NO_COMPACTION 2u /* diagnostic: skip the mid-ray block compaction */
+
+typedef struct bh8_camera {
+  double pos[3];    /* Camera::focus() */
+  double vx[3];     /* Object::vector_x() (viewing direction) */
+  double vy[3];     /* Object::vector_y() */
+  double vz[3];     /* Object::vector_z() */
+  double focus_len; /* width / (2 tan(fov/2)), camera.h:40 */
+  int32_t width;
+  int32_t height;
+} bh8_camera;
+
+typedef struct bh8_object {
+  int32_t kind;        /* BH8_KIND_* */
+  int32_t key;         /* ObjectManager key (insertion index), reported back in the key map */
+  int32_t tex_id;      /* texture slot for ANNULUS / RECTANGLE, -1 = none */
+  int32_t pattern;     /* BH8_PATTERN_* for INFINITE_PLANE */
+  double v[5][3];      /* Object::vertex()[0..4]; [0] is position()/center(), corners are [1..4] */
+  double n[3];         /* ANNULUS: norm_ (fixed at construction); INFINITE_PLANE: vector_z() */
+  double ex[3];        /* INFINITE_PLANE: vector_x() */
+  double ey[3];        /* INFINITE_PLANE: vector_y() */
+  double r_in;         /* ANNULUS r_inner_ */
+  double r_out;        /* ANNULUS r_outer_ */
+  double mass;         /* BLACKHOLE mass() */
+  double pattern_size; /* CHESS pattern_size_ */
+} bh8_object;
+
+typedef struct bh8_scene {
+  int32_t n_obj;         /* <= BH8_MAX_OBJECTS, listed in ObjectManager iteration order */
+  int32_t bh_index;      /* index in obj[] of the black hole the geodesics bend around */
+  const bh8_object* obj;
+} bh8_scene;
+
+typedef struct bh8_params {
+  int32_t nstep;         /* the literal 20 at blackhole_solution_test.cc:202; legs run nstep-1 steps */
+  int32_t pixel_format;  /* BH8_PIXEL_* */
+  uint32_t flags;        /* BH8_FLAG_* */
+  /* Row-stripe sharding of one frame across devices / ranks: stripes of stripe_rows rows are dealt
+   * round-robin, this call renders stripes s with s % shard_count == shard_index into the
+   * full-frame buffer.  stripe_rows = 0 or shard_count <= 1 renders the whole frame. */
+  int32_t stripe_rows;
+  int32_t shard_index;
+  int32_t shard_count;
+} bh8_params;
+
+typedef struct bh8_stats {
+  uint64_t rays;         /* rays traced by this call */
+  uint64_t steps;        /* geodesic updates executed (reference definition: per-ray count of
+                            u/phi updates up to and including the one whose segment hit) */
+  uint64_t class_count[4];
+  uint64_t tex_oob;      /* texture fetches whose reference index lay outside the image (clamped) */
+  double kernel_ms;      /* device time of the render kernel(s), CUDA events, max over devices */
+  double total_ms;       /* host wall time of the call */
+} bh8_stats;
+
+typedef struct bh8_ctx bh8_ctx;
+
+/* Create a context driving n_dev CUDA devices (devices[i] = ordinal; NULL = {0..n_dev-1}).
+ * With n_dev > 1 peer access to devices[0] is enabled and frames are gathered there. */
+int bh8_create(bh8_ctx** out, const int* devices, int n_dev);
+void bh8_destroy(bh8_ctx* ctx);
+const char* bh8_last_error(const bh8_ctx* ctx); /* ctx may be NULL: error of the failed bh8_create */
+int bh8_abi_version(void);
+
+/* Copy a CV_8UC3 BGR image (Material::texture_) into slot tex_id on every device of the context. */
+int bh8_set_texture(bh8_ctx* ctx, int tex_id, const uint8_t* bgr, int rows, int cols,
+                    size_t row_stride_bytes);
+
+/* Render n_frames frames.  scenes[f] / cams[f] are the snapshots for frame f (host memory).
+ * out_pixels: HOST buffer of n_frames * H * W * bpp bytes; out_class / out_key (nullable): HOST
+ * buffers of n_frames * H * W bytes (hit class; ObjectManager key of the hit object, -1 = none);
+ * out_steps (nullable): n_frames * H * W uint16 step counts.  Synchronous; includes the
+ * host<->device copies.  With several devices whole frames are dealt round-robin when
+ * n_frames >= n_dev, else each frame is striped over the devices (params->stripe_rows, default 16). */
+int bh8_render(bh8_ctx* ctx, const bh8_scene* scenes, const bh8_camera* cams, int n_frames,
+               const bh8_params* params, uint8_t* out_pixels, uint8_t* out_class, int8_t* out_key,
+               uint16_t* out_steps, bh8_stats* stats);
+
+/* Device-resident path (device 0 of the context).  d_pixels / d_class / d_key / d_steps are DEVICE
+ * pointers for ONE frame -- they may be peer / IPC mappings of another GPU's memory, in which case
+ * the kernel's stores go over NVLink and no separate gather copy is needed.  Asynchronous on the
+ * context's stream; bh8_sync() waits.  The scene/camera snapshot (a few hundred bytes) is passed
+ * as kernel parameters, so nothing else has to be resident. */
+int bh8_render_device(bh8_ctx* ctx, const bh8_scene* scene, const bh8_camera* cam,
+                      const bh8_params* params, void* d_pixels, void* d_class, void* d_key,
+                      void* d_steps);
+int bh8_sync(bh8_ctx* ctx);
+/* Device time in ms between the first and the last kernel of the bh8_render_device() calls issued
+ * since the previous bh8_timer_begin(); call after bh8_sync(). */
+int bh8_timer_begin(bh8_ctx* ctx);
+int bh8_timer_end_ms(bh8_ctx* ctx, double* ms);
+/* Read (and reset) the device-side counters accumulated by BH8_FLAG_STATS launches. */
+int bh8_read_stats(bh8_ctx* ctx, bh8_stats* stats);
+/* Number of kernels this context has launched so far (the bench's gpu_launches claim). */
+uint64_t bh8_launch_count(const bh8_ctx* ctx);
+
+/* Frame buffers owned by the library (cudaMalloc on device 0 of the context) and their CUDA IPC
+ * handles, for one-process-per-GPU sharding: rank 0 allocates and exports, the other ranks import
+ * and pass the mapping to bh8_render_device(). */
+int bh8_frame_alloc(bh8_ctx* ctx, size_t bytes, void** d_ptr);
+int bh8_frame_free(bh8_ctx* ctx, void* d_ptr);
+int bh8_ipc_export(bh8_ctx* ctx, void* d_ptr, uint8_t handle[64]);
+int bh8_ipc_import(bh8_ctx* ctx, const uint8_t handle[64], void** d_ptr);
+int bh8_ipc_close(bh8_ctx* ctx, void* d_ptr);
+int bh8_memcpy_d2h(bh8_ctx* ctx, void* host, const void* d_ptr, size_t bytes);
+int bh8_memset_d(bh8_ctx* ctx, void* d_ptr, int value, size_t bytes);
+
+/* FP64 pipe peak: runs a dependent-free DFMA chain on every SM of device 0 and reports the
+ * sustained FP64 FLOP/s (FMA = 2) -- the roofline denominator for this path. */
+int bh8_measure_fp64_peak(bh8_ctx* ctx, double* flops_per_s, double* seconds_run);
+
+size_t bh8_pixel_bytes(int pixel_format);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* BH8_H_ */
