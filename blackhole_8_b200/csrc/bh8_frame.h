@@ -1,0 +1,247 @@
+// bh8_frame.h -- per-frame constants of the geodesic render kernel and the host code that
+// derives them from a bh8_scene / bh8_camera snapshot.
+//
+// Everything a ray needs that does not depend on the pixel is hoisted here once per frame on the
+// host (the reference recomputes all of it per pixel or per step: F at blackhole_solution_test.cc:168,
+// Rectangle's normal at vector_object.h:108-111, 1/(b*b) at blackhole_solution.h:28, ...).  The struct
+// travels to the GPU as a __grid_constant__ kernel parameter, so its fields are constant-bank
+// operands of the FP64 instructions: no loads in the stepping loop.
+#ifndef BH8_FRAME_H_
+#define BH8_FRAME_H_
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "bh8.h"
+
+#define BH8_BISECT_ITERS 20  /* static const int count = 20, blackhole_solution.h:36 */
+
+struct Bh8Obj {
+  int32_t kind, key, cls, tex;  // tex = texture slot or -1
+  int32_t pattern, central, tex_rows, tex_cols;
+  double n[3];    // unit normal Collide() uses: Annulus norm_; Rectangle normalize(e1 x e3); plane vector_z
+  double p0[3];   // point of the plane: Annulus center() / Rectangle vertex()[1] / plane position(); BH centre
+  double d;       // n . p0
+  double c_bh;    // n . (bh_pos - p0): signed distance of the black hole from the plane (0 => central)
+  double e1[3], e3[3], e1e1, e3e3;  // Rectangle edges vertex()[2]-[1], vertex()[4]-[1]
+  double r_in, r_out;               // Annulus radii
+  double t0[3], s1[3];              // texture frame (Rectangle::color): origin vertex()[1], s1 = [2]-[1]
+  double inv_s1s1;                  // 1 / (s1 . s1)
+  double kw, kh;                    // cols / (s1 . s1),  rows / |s2|
+  double ex0, ex1, ey0, ey1, psize; // InfinitePlane::color coefficients, ChessPattern2D size
+};
+
+struct Bh8Frame {
+  // camera (camera.h:55-63)
+  double cam[3], fv[3], vy[3], vz[3];
+  double half_w, half_h;  // width/2.0, height/2.0
+  int32_t width, height;
+  // black hole (blackhole_solution.h:24-57)
+  double bh[3], F[3];     // F = camera.focus() - blackhole.position()
+  double FF;              // F . F
+  double mass, two_m, b_c2 /* b_c^2 */, inv3m, R, R2;
+  double r0, u0;          // |F| and 1/|F|: convertedCameraFocus has the length of F
+  double bis_mid0;                    // first bisection midpoint
+  double bis_h[BH8_BISECT_ITERS + 1]; // bis_h[i] = (r - l) / 2^(i+1): +- offset applied after test i-1; [20] = final width
+  // integration
+  int32_t nstep, n_obj, bh_index, n_central;
+  double inv_nstep;
+  // conservative filters (see bh8_ray.cuh)
+  double u_gate;        // non-central planes can only be crossed while min(u) <= u_gate
+  double u_horizon;     // horizon sphere cannot be reached while u <= u_horizon and |dphi| <= 1
+  uint32_t cam_mask;    // sign bits of n.cam - d per object (state of the first segment's start)
+  uint32_t noncentral_mask;  // objects handled by the sign-mask filter
+  uint32_t central_mask;     // objects handled by the phi-crossing filter
+  int32_t first_resolve;     // 1: always resolve the first segment exactly (camera too close / in a plane)
+  // output
+  int32_t pixel_format, stripe_rows, shard_index, shard_count;
+  uint32_t flags;
+  Bh8Obj obj[BH8_MAX_OBJECTS];
+};
+
+#if !defined(__CUDACC__) || defined(BH8_HOST_BUILD)
+// ---- host side: snapshot -> Bh8Frame --------------------------------------------------------
+
+static inline double bh8h_dot(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline void bh8h_sub(double* r, const double* a, const double* b) {
+  for (int i = 0; i < 3; ++i) r[i] = a[i] - b[i];
+}
+static inline void bh8h_cross(double* r, const double* a, const double* b) {
+  r[0] = a[1] * b[2] - a[2] * b[1];
+  r[1] = a[2] * b[0] - a[0] * b[2];
+  r[2] = a[0] * b[1] - a[1] * b[0];
+}
+static inline void bh8h_normalize(double* v) {  // cv::normalize semantics: zero stays zero
+  const double n = sqrt(bh8h_dot(v, v));
+  const double s = n ? 1. / n : 0.;
+  for (int i = 0; i < 3; ++i) v[i] *= s;
+}
+
+// tex_rows/tex_cols: sizes of the texture slots (0 = slot empty).  Returns BH8_OK or an error code
+// and a message in err (>= 160 bytes).
+static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
+                                  const int* tex_rows, const int* tex_cols, Bh8Frame* f, char* err) {
+#define BH8_FAIL(code, msg) \
+  do {                      \
+    strcpy(err, msg);       \
+    return code;            \
+  } while (0)
+  if (!scene || !cam || !prm || !scene->obj) BH8_FAIL(BH8_EINVAL, "null scene / camera / params");
+  if (scene->n_obj < 1 || scene->n_obj > BH8_MAX_OBJECTS) BH8_FAIL(BH8_EINVAL, "n_obj out of range");
+  if (scene->bh_index < 0 || scene->bh_index >= scene->n_obj ||
+      scene->obj[scene->bh_index].kind != BH8_KIND_BLACKHOLE)
+    BH8_FAIL(BH8_EINVAL, "bh_index does not name a BH8_KIND_BLACKHOLE object");
+  if (cam->width < 1 || cam->height < 1 || cam->width > 65536 || cam->height > 65536)
+    BH8_FAIL(BH8_EINVAL, "camera size out of range");
+  if (prm->nstep < 2 || prm->nstep > 32767) BH8_FAIL(BH8_EINVAL, "nstep must be in [2, 32767]");
+  if (prm->pixel_format < 0 || prm->pixel_format > BH8_PIXEL_BGR8) BH8_FAIL(BH8_EINVAL, "bad pixel_format");
+  const bh8_object* bho = &scene->obj[scene->bh_index];
+  if (!(bho->mass > 0)) BH8_FAIL(BH8_EINVAL, "black hole mass must be positive");
+
+  memset(f, 0, sizeof *f);
+  for (int i = 0; i < 3; ++i) {
+    f->cam[i] = cam->pos[i];
+    f->fv[i] = cam->vx[i] * cam->focus_len;  // Camera::focus_vector, camera.h:61-63
+    f->vy[i] = cam->vy[i];
+    f->vz[i] = cam->vz[i];
+    f->bh[i] = bho->v[0][i];
+  }
+  f->half_w = cam->width / 2.0;
+  f->half_h = cam->height / 2.0;
+  f->width = cam->width;
+  f->height = cam->height;
+  bh8h_sub(f->F, f->cam, f->bh);
+  f->FF = bh8h_dot(f->F, f->F);
+  f->mass = bho->mass;
+  f->two_m = 2.0 * bho->mass;
+  const double b_c = 3.0 * sqrt(3.0) * bho->mass;  // blackhole_solution.h:25
+  f->b_c2 = b_c * b_c;
+  f->inv3m = 1.0 / (3.0 * bho->mass);
+  f->R = 2 * bho->mass;  // radius(), blackhole_solution.h:57
+  f->R2 = f->R * f->R;
+  f->r0 = sqrt(f->FF);
+  f->u0 = 1. / f->r0;
+  {  // SolveG's interval, blackhole_solution.h:37-38; utility.h:17-21
+    const double l = 0.0 + cbrt(2.220446049250313e-16);
+    const double r = f->inv3m;
+    f->bis_mid0 = (l + r) / 2.0;
+    double h = (r - l) / 2.0;
+    for (int i = 0; i <= BH8_BISECT_ITERS; ++i) {
+      h /= 2.0;
+      f->bis_h[i] = h;  // bis_h[i] = (r-l)/2^(i+2)
+    }
+  }
+  f->nstep = prm->nstep;
+  f->inv_nstep = 1.0 / prm->nstep;
+  f->n_obj = scene->n_obj;
+  f->bh_index = scene->bh_index;
+  f->pixel_format = prm->pixel_format;
+  f->stripe_rows = prm->stripe_rows;
+  f->shard_index = prm->shard_index;
+  f->shard_count = prm->shard_count;
+  f->flags = prm->flags;
+  if (f->shard_count > 1 && (f->shard_index < 0 || f->shard_index >= f->shard_count || f->stripe_rows < 1))
+    BH8_FAIL(BH8_EINVAL, "bad stripe sharding parameters");
+
+  double min_dist = INFINITY;
+  for (int k = 0; k < scene->n_obj; ++k) {
+    const bh8_object* o = &scene->obj[k];
+    Bh8Obj* q = &f->obj[k];
+    q->kind = o->kind;
+    q->key = o->key;
+    q->tex = -1;
+    q->pattern = o->pattern;
+    switch (o->kind) {
+      case BH8_KIND_BLACKHOLE:
+        q->cls = BH8_CLASS_HORIZON;
+        if (k != scene->bh_index)
+          BH8_FAIL(BH8_EUNSUPPORTED, "more than one black hole in a scene is not supported");
+        for (int i = 0; i < 3; ++i) q->p0[i] = o->v[0][i];
+        continue;
+      case BH8_KIND_ANNULUS:
+        q->cls = BH8_CLASS_DISC;
+        for (int i = 0; i < 3; ++i) {
+          q->n[i] = o->n[i];          // norm_, vector_object.h:325 (not re-normalised here: as stored)
+          q->p0[i] = o->v[0][i];      // center(), :349
+        }
+        q->r_in = o->r_in;
+        q->r_out = o->r_out;
+        break;
+      case BH8_KIND_RECTANGLE:
+        q->cls = BH8_CLASS_OBJECT;
+        for (int i = 0; i < 3; ++i) q->p0[i] = o->v[1][i];  // vector_object.h:108
+        bh8h_sub(q->e1, o->v[2], o->v[1]);
+        bh8h_sub(q->e3, o->v[4], o->v[1]);
+        bh8h_cross(q->n, q->e1, q->e3);
+        bh8h_normalize(q->n);  // :111
+        q->e1e1 = bh8h_dot(q->e1, q->e1);
+        q->e3e3 = bh8h_dot(q->e3, q->e3);
+        break;
+      case BH8_KIND_INFINITE_PLANE:
+        q->cls = BH8_CLASS_OBJECT;
+        if (o->pattern != BH8_PATTERN_BLACK && o->pattern != BH8_PATTERN_CHESS)
+          BH8_FAIL(BH8_EUNSUPPORTED, "InfinitePlane pattern is not BLACK or CHESS (opaque std::function)");
+        for (int i = 0; i < 3; ++i) {
+          q->n[i] = o->n[i];      // vector_z(), vector_object.h:211
+          q->p0[i] = o->v[0][i];  // position()
+        }
+        q->ex0 = o->ex[0];
+        q->ex1 = o->ex[1];
+        q->ey0 = o->ey[0];
+        q->ey1 = o->ey[1];
+        q->psize = o->pattern_size;
+        if (o->pattern == BH8_PATTERN_CHESS && !((int)(o->pattern_size * 2) != 0))
+          BH8_FAIL(BH8_EINVAL, "chess pattern_size too small: (int)(2*size) == 0 divides by zero in the reference");
+        break;
+      default:
+        BH8_FAIL(BH8_EUNSUPPORTED, "object kind not supported by the GPU path (Triangle/Sphere/Cylinder)");
+    }
+    q->d = bh8h_dot(q->n, q->p0);
+    {
+      double w[3];
+      bh8h_sub(w, f->bh, q->p0);
+      q->c_bh = bh8h_dot(q->n, w);
+    }
+    q->central = (q->c_bh == 0.0);
+    if (o->kind == BH8_KIND_ANNULUS || o->kind == BH8_KIND_RECTANGLE) {
+      double s2[3];
+      for (int i = 0; i < 3; ++i) q->t0[i] = o->v[1][i];  // vector_object.h:164-166
+      bh8h_sub(q->s1, o->v[2], o->v[1]);
+      bh8h_sub(s2, o->v[4], o->v[1]);
+      const double s1s1 = bh8h_dot(q->s1, q->s1);
+      q->inv_s1s1 = 1.0 / s1s1;
+      if (o->tex_id >= 0) {
+        if (o->tex_id >= BH8_MAX_TEXTURES || !tex_rows || tex_rows[o->tex_id] <= 0)
+          BH8_FAIL(BH8_EINVAL, "object refers to a texture slot that was never set");
+        q->tex = o->tex_id;
+        q->tex_rows = tex_rows[o->tex_id];
+        q->tex_cols = tex_cols[o->tex_id];
+        q->kw = q->tex_cols / s1s1;
+        q->kh = q->tex_rows / sqrt(bh8h_dot(s2, s2));
+      }
+    }
+    const double side_cam = bh8h_dot(q->n, f->cam) - q->d;
+    if (side_cam < 0) f->cam_mask |= 1u << k;
+    if (side_cam == 0) f->first_resolve = 1;
+    if (q->central) {
+      f->central_mask |= 1u << k;
+      f->n_central++;
+    } else {
+      f->noncentral_mask |= 1u << k;
+      if (fabs(q->c_bh) < min_dist) min_dist = fabs(q->c_bh);
+    }
+  }
+  // A chord between two points of the ray stays inside radius max(r1,r2); a plane at distance D
+  // from the hole can only be met when max(r1,r2) >= D, i.e. min(u1,u2) <= 1/D (small margin).
+  f->u_gate = f->noncentral_mask ? (1.0 + 1e-9) / min_dist : -1.0;
+  // Horizon sphere R = 2M: a chord whose ends are both outside 1.5R and subtend <= 1 rad stays
+  // outside R (1.5 cos(0.5) = 1.316 > 1).
+  f->u_horizon = 1.0 / (1.5 * f->R * (1.0 + 1e-9));
+  if (!(f->u0 <= f->u_horizon)) f->first_resolve = 1;
+  return BH8_OK;
+#undef BH8_FAIL
+}
+#endif  // host
+
+#endif  // BH8_FRAME_H_

@@ -1,0 +1,589 @@
+// bh8_lib.cu -- the C ABI of include/bh8.h: contexts, textures, launches, copies.
+//
+// Host side of the boundary that replaces the inline pixel loop of
+// blackhole_solution_test.cc:161-308.  No CPU rendering path exists in this library: every entry
+// point that produces pixels launches bh8_render_kernel on a CUDA device or fails.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#define BH8_HOST_BUILD 1
+#include "bh8_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Device {
+  int ordinal = 0;
+  cudaStream_t stream = nullptr;       // kernels
+  cudaStream_t copy_stream = nullptr;  // D2H of finished frames
+  cudaArray_t tex_array[BH8_MAX_TEXTURES] = {};
+  cudaTextureObject_t tex_obj[BH8_MAX_TEXTURES] = {};
+  unsigned long long* d_stats = nullptr;  // 8 counters
+  // double-buffered frame staging for bh8_render()
+  void* d_pix[2] = {nullptr, nullptr};
+  uint8_t* d_cls[2] = {nullptr, nullptr};
+  int8_t* d_key[2] = {nullptr, nullptr};
+  uint16_t* d_steps[2] = {nullptr, nullptr};
+  size_t cap_pixels = 0;  // pixels each staging buffer can hold
+  cudaEvent_t ev_kernel_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copy_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  bool timing_open = false;
+};
+
+}  // namespace
+
+struct bh8_ctx {
+  int n_dev = 0;
+  Device dev[BH8_MAX_DEVICES];
+  int tex_rows[BH8_MAX_TEXTURES] = {};
+  int tex_cols[BH8_MAX_TEXTURES] = {};
+  std::string err;
+  uint64_t launches = 0;
+  std::vector<void*> owned;  // bh8_frame_alloc results (device 0)
+};
+
+namespace {
+
+int fail(bh8_ctx* ctx, int code, const std::string& msg) {
+  if (ctx)
+    ctx->err = msg;
+  else
+    g_create_error = msg;
+  return code;
+}
+
+#define BH8_CUDA(ctx, call)                                                                     \
+  do {                                                                                          \
+    const cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(ctx, BH8_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+  } while (0)
+
+struct Launch {
+  bh8::Bh8Out out;
+  dim3 grid;
+};
+
+// Grid for the rows this shard renders (see the kernel's tile-origin computation).
+int make_grid(const Bh8Frame& f, dim3* grid) {
+  const int gx = (f.width + bh8::kTileW - 1) / bh8::kTileW;
+  int gy;
+  if (f.shard_count > 1) {
+    if (f.stripe_rows % bh8::kTileH != 0) return BH8_EINVAL;
+    const int n_stripes = (f.height + f.stripe_rows - 1) / f.stripe_rows;
+    const int n_local = (n_stripes - f.shard_index + f.shard_count - 1) / f.shard_count;
+    gy = n_local * (f.stripe_rows / bh8::kTileH);
+  } else {
+    gy = (f.height + bh8::kTileH - 1) / bh8::kTileH;
+  }
+  *grid = dim3(gx, gy > 0 ? gy : 0, 1);
+  return BH8_OK;
+}
+
+int launch_frame(bh8_ctx* ctx, Device& d, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
+                 void* d_pixels, void* d_cls, void* d_key, void* d_steps) {
+  Bh8Frame f;
+  char msg[192];
+  const int rc = bh8_build_frame(scene, cam, prm, ctx->tex_rows, ctx->tex_cols, &f, msg);
+  if (rc != BH8_OK) return fail(ctx, rc, msg);
+  dim3 grid;
+  if (make_grid(f, &grid) != BH8_OK)
+    return fail(ctx, BH8_EINVAL, "stripe_rows must be a multiple of 8 when shard_count > 1");
+  if (!d_pixels) return fail(ctx, BH8_EINVAL, "null pixel buffer");
+  if (grid.y == 0) return BH8_OK;
+  bh8::Bh8Tex tex;
+  for (int i = 0; i < BH8_MAX_TEXTURES; ++i) tex.obj[i] = d.tex_obj[i];
+  bh8::Bh8Out out;
+  out.pixels = static_cast<uint8_t*>(d_pixels);
+  out.cls = static_cast<uint8_t*>(d_cls);
+  out.key = static_cast<int8_t*>(d_key);
+  out.steps = static_cast<uint16_t*>(d_steps);
+  out.stats = d.d_stats;
+  out.vec_ok = (f.width % 4 == 0) && (reinterpret_cast<uintptr_t>(d_pixels) % 16 == 0) &&
+               f.pixel_format != BH8_PIXEL_BGR8;
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  if (prm->flags & BH8_FLAG_NO_COMPACTION)
+    bh8::bh8_render_kernel<false><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out);
+  else
+    bh8::bh8_render_kernel<true><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out);
+  BH8_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return BH8_OK;
+}
+
+int ensure_staging(bh8_ctx* ctx, Device& d, size_t pixels) {
+  if (d.cap_pixels >= pixels) return BH8_OK;
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  BH8_CUDA(ctx, cudaDeviceSynchronize());
+  for (int b = 0; b < 2; ++b) {
+    cudaFree(d.d_pix[b]);
+    cudaFree(d.d_cls[b]);
+    cudaFree(d.d_key[b]);
+    cudaFree(d.d_steps[b]);
+    d.d_pix[b] = nullptr;
+    d.d_cls[b] = nullptr;
+    d.d_key[b] = nullptr;
+    d.d_steps[b] = nullptr;
+  }
+  d.cap_pixels = 0;
+  for (int b = 0; b < 2; ++b) {
+    BH8_CUDA(ctx, cudaMalloc(&d.d_pix[b], pixels * 4));
+    BH8_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d.d_cls[b]), pixels));
+    BH8_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d.d_key[b]), pixels));
+    BH8_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d.d_steps[b]), pixels * 2));
+  }
+  d.cap_pixels = pixels;
+  return BH8_OK;
+}
+
+int read_stats(bh8_ctx* ctx, bh8_stats* s) {
+  for (int i = 0; i < ctx->n_dev; ++i) {
+    Device& d = ctx->dev[i];
+    unsigned long long h[8];
+    BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+    BH8_CUDA(ctx, cudaMemcpyAsync(h, d.d_stats, sizeof h, cudaMemcpyDeviceToHost, d.stream));
+    BH8_CUDA(ctx, cudaMemsetAsync(d.d_stats, 0, sizeof h, d.stream));
+    BH8_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    s->rays += h[0];
+    s->steps += h[1];
+    for (int c = 0; c < 4; ++c) s->class_count[c] += h[2 + c];
+    s->tex_oob += h[6];
+  }
+  return BH8_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bh8_abi_version(void) { return BH8_ABI_VERSION; }
+
+size_t bh8_pixel_bytes(int pixel_format) { return pixel_format == BH8_PIXEL_BGR8 ? 3 : 4; }
+
+const char* bh8_last_error(const bh8_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+uint64_t bh8_launch_count(const bh8_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int bh8_create(bh8_ctx** out, const int* devices, int n_dev) {
+  if (!out || n_dev < 1 || n_dev > BH8_MAX_DEVICES) return fail(nullptr, BH8_EINVAL, "bad arguments to bh8_create");
+  *out = nullptr;
+  int count = 0;
+  const cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count < 1)
+    return fail(nullptr, BH8_ENODEVICE,
+                std::string("no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+  bh8_ctx* ctx = new (std::nothrow) bh8_ctx();
+  if (!ctx) return fail(nullptr, BH8_ENOMEM, "out of host memory");
+  ctx->n_dev = n_dev;
+  for (int i = 0; i < n_dev; ++i) {
+    Device& d = ctx->dev[i];
+    d.ordinal = devices ? devices[i] : i;
+    if (d.ordinal < 0 || d.ordinal >= count) {
+      delete ctx;
+      return fail(nullptr, BH8_EINVAL, "device ordinal out of range");
+    }
+  }
+#define BH8_CREATE_CUDA(call)                                                                  \
+  do {                                                                                         \
+    const cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                                  \
+      const std::string m__ = std::string(#call) + ": " + cudaGetErrorString(e__);             \
+      bh8_destroy(ctx);                                                                        \
+      return fail(nullptr, BH8_ECUDA, m__);                                                    \
+    }                                                                                          \
+  } while (0)
+  for (int i = 0; i < n_dev; ++i) {
+    Device& d = ctx->dev[i];
+    BH8_CREATE_CUDA(cudaSetDevice(d.ordinal));
+    cudaDeviceProp prop;
+    BH8_CREATE_CUDA(cudaGetDeviceProperties(&prop, d.ordinal));
+    if (prop.major < 10) {
+      bh8_destroy(ctx);
+      return fail(nullptr, BH8_ENODEVICE, "device is not sm_100 (Blackwell B200); the kernels are sm_100a only");
+    }
+    BH8_CREATE_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    BH8_CREATE_CUDA(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+    BH8_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.d_stats), 8 * sizeof(unsigned long long)));
+    BH8_CREATE_CUDA(cudaMemset(d.d_stats, 0, 8 * sizeof(unsigned long long)));
+    for (int b = 0; b < 2; ++b) {
+      BH8_CREATE_CUDA(cudaEventCreateWithFlags(&d.ev_kernel_done[b], cudaEventDisableTiming));
+      BH8_CREATE_CUDA(cudaEventCreateWithFlags(&d.ev_copy_done[b], cudaEventDisableTiming));
+    }
+    BH8_CREATE_CUDA(cudaEventCreate(&d.ev_t0));
+    BH8_CREATE_CUDA(cudaEventCreate(&d.ev_t1));
+    // Frames are gathered on device 0: the other devices store into its memory over NVLink.
+    if (i > 0) {
+      int can = 0;
+      BH8_CREATE_CUDA(cudaDeviceCanAccessPeer(&can, d.ordinal, ctx->dev[0].ordinal));
+      if (!can) {
+        bh8_destroy(ctx);
+        return fail(nullptr, BH8_ECUDA, "no peer access to device 0 of the context");
+      }
+      const cudaError_t pe = cudaDeviceEnablePeerAccess(ctx->dev[0].ordinal, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) BH8_CREATE_CUDA(pe);
+      (void)cudaGetLastError();
+    }
+  }
+#undef BH8_CREATE_CUDA
+  *out = ctx;
+  return BH8_OK;
+}
+
+void bh8_destroy(bh8_ctx* ctx) {
+  if (!ctx) return;
+  for (int i = 0; i < ctx->n_dev; ++i) {
+    Device& d = ctx->dev[i];
+    if (cudaSetDevice(d.ordinal) != cudaSuccess) continue;
+    cudaDeviceSynchronize();
+    for (int t = 0; t < BH8_MAX_TEXTURES; ++t) {
+      if (d.tex_obj[t]) cudaDestroyTextureObject(d.tex_obj[t]);
+      if (d.tex_array[t]) cudaFreeArray(d.tex_array[t]);
+    }
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(d.d_pix[b]);
+      cudaFree(d.d_cls[b]);
+      cudaFree(d.d_key[b]);
+      cudaFree(d.d_steps[b]);
+      if (d.ev_kernel_done[b]) cudaEventDestroy(d.ev_kernel_done[b]);
+      if (d.ev_copy_done[b]) cudaEventDestroy(d.ev_copy_done[b]);
+    }
+    if (d.ev_t0) cudaEventDestroy(d.ev_t0);
+    if (d.ev_t1) cudaEventDestroy(d.ev_t1);
+    cudaFree(d.d_stats);
+    if (i == 0)
+      for (void* p : ctx->owned) cudaFree(p);
+    if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+  }
+  delete ctx;
+}
+
+int bh8_set_texture(bh8_ctx* ctx, int tex_id, const uint8_t* bgr, int rows, int cols, size_t row_stride_bytes) {
+  if (!ctx) return BH8_EINVAL;
+  if (tex_id < 0 || tex_id >= BH8_MAX_TEXTURES || !bgr || rows < 1 || cols < 1 || rows > 32768 || cols > 32768)
+    return fail(ctx, BH8_EINVAL, "bad texture arguments");
+  if (row_stride_bytes == 0) row_stride_bytes = static_cast<size_t>(cols) * 3;
+  if (row_stride_bytes < static_cast<size_t>(cols) * 3) return fail(ctx, BH8_EINVAL, "row stride smaller than a row");
+  // cv::Mat CV_8UC3 (B,G,R) -> uchar4 texels (B,G,R,255)
+  std::vector<uchar4> texels(static_cast<size_t>(rows) * cols);
+  for (int r = 0; r < rows; ++r) {
+    const uint8_t* src = bgr + static_cast<size_t>(r) * row_stride_bytes;
+    uchar4* dst = texels.data() + static_cast<size_t>(r) * cols;
+    for (int c = 0; c < cols; ++c) dst[c] = make_uchar4(src[3 * c], src[3 * c + 1], src[3 * c + 2], 255);
+  }
+  for (int i = 0; i < ctx->n_dev; ++i) {
+    Device& d = ctx->dev[i];
+    BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+    BH8_CUDA(ctx, cudaDeviceSynchronize());
+    if (d.tex_obj[tex_id]) {
+      cudaDestroyTextureObject(d.tex_obj[tex_id]);
+      d.tex_obj[tex_id] = 0;
+    }
+    if (d.tex_array[tex_id]) {
+      cudaFreeArray(d.tex_array[tex_id]);
+      d.tex_array[tex_id] = nullptr;
+    }
+    const cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+    BH8_CUDA(ctx, cudaMallocArray(&d.tex_array[tex_id], &desc, cols, rows));
+    BH8_CUDA(ctx, cudaMemcpy2DToArray(d.tex_array[tex_id], 0, 0, texels.data(), static_cast<size_t>(cols) * 4,
+                                      static_cast<size_t>(cols) * 4, rows, cudaMemcpyHostToDevice));
+    cudaResourceDesc res;
+    std::memset(&res, 0, sizeof res);
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = d.tex_array[tex_id];
+    cudaTextureDesc td;
+    std::memset(&td, 0, sizeof td);
+    td.addressMode[0] = cudaAddressModeClamp;
+    td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;       // nearest texel, like the reference's truncation
+    td.readMode = cudaReadModeElementType;     // raw bytes
+    td.normalizedCoords = 0;
+    BH8_CUDA(ctx, cudaCreateTextureObject(&d.tex_obj[tex_id], &res, &td, nullptr));
+  }
+  ctx->tex_rows[tex_id] = rows;
+  ctx->tex_cols[tex_id] = cols;
+  return BH8_OK;
+}
+
+int bh8_render_device(bh8_ctx* ctx, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* params,
+                      void* d_pixels, void* d_class, void* d_key, void* d_steps) {
+  if (!ctx) return BH8_EINVAL;
+  return launch_frame(ctx, ctx->dev[0], scene, cam, params, d_pixels, d_class, d_key, d_steps);
+}
+
+int bh8_sync(bh8_ctx* ctx) {
+  if (!ctx) return BH8_EINVAL;
+  for (int i = 0; i < ctx->n_dev; ++i) {
+    BH8_CUDA(ctx, cudaSetDevice(ctx->dev[i].ordinal));
+    BH8_CUDA(ctx, cudaStreamSynchronize(ctx->dev[i].stream));
+    BH8_CUDA(ctx, cudaStreamSynchronize(ctx->dev[i].copy_stream));
+  }
+  return BH8_OK;
+}
+
+int bh8_timer_begin(bh8_ctx* ctx) {
+  if (!ctx) return BH8_EINVAL;
+  Device& d = ctx->dev[0];
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  BH8_CUDA(ctx, cudaEventRecord(d.ev_t0, d.stream));
+  d.timing_open = true;
+  return BH8_OK;
+}
+
+int bh8_timer_end_ms(bh8_ctx* ctx, double* ms) {
+  if (!ctx || !ms) return BH8_EINVAL;
+  Device& d = ctx->dev[0];
+  if (!d.timing_open) return fail(ctx, BH8_EINVAL, "bh8_timer_end_ms without bh8_timer_begin");
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  BH8_CUDA(ctx, cudaEventRecord(d.ev_t1, d.stream));
+  BH8_CUDA(ctx, cudaEventSynchronize(d.ev_t1));
+  float f = 0;
+  BH8_CUDA(ctx, cudaEventElapsedTime(&f, d.ev_t0, d.ev_t1));
+  *ms = f;
+  d.timing_open = false;
+  return BH8_OK;
+}
+
+int bh8_read_stats(bh8_ctx* ctx, bh8_stats* stats) {
+  if (!ctx || !stats) return BH8_EINVAL;
+  std::memset(stats, 0, sizeof *stats);
+  return read_stats(ctx, stats);
+}
+
+int bh8_render(bh8_ctx* ctx, const bh8_scene* scenes, const bh8_camera* cams, int n_frames, const bh8_params* params,
+               uint8_t* out_pixels, uint8_t* out_class, int8_t* out_key, uint16_t* out_steps, bh8_stats* stats) {
+  if (!ctx) return BH8_EINVAL;
+  if (!scenes || !cams || !params || !out_pixels || n_frames < 1) return fail(ctx, BH8_EINVAL, "bad arguments to bh8_render");
+  const auto wall0 = std::chrono::steady_clock::now();
+  const size_t bpp = bh8_pixel_bytes(params->pixel_format);
+  size_t max_pixels = 0;
+  for (int fi = 0; fi < n_frames; ++fi) {
+    const size_t p = static_cast<size_t>(cams[fi].width) * cams[fi].height;
+    if (cams[fi].width != cams[0].width || cams[fi].height != cams[0].height)
+      return fail(ctx, BH8_EINVAL, "all frames of one bh8_render call must have the same size");
+    if (p > max_pixels) max_pixels = p;
+  }
+  const size_t npx = max_pixels;
+  const bool striped = ctx->n_dev > 1 && n_frames < ctx->n_dev;
+  const int n_active = striped ? ctx->n_dev : (n_frames < ctx->n_dev ? n_frames : ctx->n_dev);
+  // In striped mode every device stores into device 0's staging buffer (peer memory).
+  for (int i = 0; i < (striped ? 1 : n_active); ++i) {
+    const int rc = ensure_staging(ctx, ctx->dev[i], npx);
+    if (rc != BH8_OK) return rc;
+  }
+  bh8_params prm = *params;
+  if (stats) prm.flags |= BH8_FLAG_STATS;
+
+  for (int i = 0; i < n_active; ++i) {
+    BH8_CUDA(ctx, cudaSetDevice(ctx->dev[i].ordinal));
+    BH8_CUDA(ctx, cudaEventRecord(ctx->dev[i].ev_t0, ctx->dev[i].stream));
+  }
+
+  if (striped) {
+    Device& d0 = ctx->dev[0];
+    for (int fi = 0; fi < n_frames; ++fi) {
+      const int b = fi & 1;
+      if (fi >= 2) {  // buffer b is free once its previous D2H finished
+        for (int i = 0; i < ctx->n_dev; ++i) {
+          BH8_CUDA(ctx, cudaSetDevice(ctx->dev[i].ordinal));
+          BH8_CUDA(ctx, cudaStreamWaitEvent(ctx->dev[i].stream, d0.ev_copy_done[b], 0));
+        }
+      }
+      bh8_params p = prm;
+      p.stripe_rows = params->stripe_rows > 0 ? params->stripe_rows : 16;
+      p.shard_count = ctx->n_dev;
+      for (int i = 0; i < ctx->n_dev; ++i) {
+        Device& d = ctx->dev[i];
+        p.shard_index = i;
+        const int rc = launch_frame(ctx, d, &scenes[fi], &cams[fi], &p, d0.d_pix[b], out_class ? d0.d_cls[b] : nullptr,
+                                    out_key ? d0.d_key[b] : nullptr, out_steps ? d0.d_steps[b] : nullptr);
+        if (rc != BH8_OK) return rc;
+        BH8_CUDA(ctx, cudaEventRecord(d.ev_kernel_done[b], d.stream));
+        BH8_CUDA(ctx, cudaSetDevice(d0.ordinal));
+        BH8_CUDA(ctx, cudaStreamWaitEvent(d0.copy_stream, d.ev_kernel_done[b], 0));
+      }
+      BH8_CUDA(ctx, cudaSetDevice(d0.ordinal));
+      BH8_CUDA(ctx, cudaMemcpyAsync(out_pixels + fi * npx * bpp, d0.d_pix[b], npx * bpp, cudaMemcpyDeviceToHost,
+                                    d0.copy_stream));
+      if (out_class)
+        BH8_CUDA(ctx, cudaMemcpyAsync(out_class + fi * npx, d0.d_cls[b], npx, cudaMemcpyDeviceToHost, d0.copy_stream));
+      if (out_key)
+        BH8_CUDA(ctx, cudaMemcpyAsync(out_key + fi * npx, d0.d_key[b], npx, cudaMemcpyDeviceToHost, d0.copy_stream));
+      if (out_steps)
+        BH8_CUDA(ctx, cudaMemcpyAsync(out_steps + fi * npx, d0.d_steps[b], npx * 2, cudaMemcpyDeviceToHost,
+                                      d0.copy_stream));
+      BH8_CUDA(ctx, cudaEventRecord(d0.ev_copy_done[b], d0.copy_stream));
+    }
+  } else {
+    // whole frames dealt round-robin; per device: kernel(f) -> D2H(f) overlaps kernel(f+1)
+    std::vector<int> issued(ctx->n_dev, 0);
+    for (int fi = 0; fi < n_frames; ++fi) {
+      Device& d = ctx->dev[fi % n_active];
+      const int b = issued[fi % n_active]++ & 1;
+      BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+      if (issued[fi % n_active] > 2) BH8_CUDA(ctx, cudaStreamWaitEvent(d.stream, d.ev_copy_done[b], 0));
+      bh8_params p = prm;
+      p.shard_count = 0;
+      p.shard_index = 0;
+      const int rc = launch_frame(ctx, d, &scenes[fi], &cams[fi], &p, d.d_pix[b], out_class ? d.d_cls[b] : nullptr,
+                                  out_key ? d.d_key[b] : nullptr, out_steps ? d.d_steps[b] : nullptr);
+      if (rc != BH8_OK) return rc;
+      BH8_CUDA(ctx, cudaEventRecord(d.ev_kernel_done[b], d.stream));
+      BH8_CUDA(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_kernel_done[b], 0));
+      BH8_CUDA(ctx, cudaMemcpyAsync(out_pixels + fi * npx * bpp, d.d_pix[b], npx * bpp, cudaMemcpyDeviceToHost,
+                                    d.copy_stream));
+      if (out_class)
+        BH8_CUDA(ctx, cudaMemcpyAsync(out_class + fi * npx, d.d_cls[b], npx, cudaMemcpyDeviceToHost, d.copy_stream));
+      if (out_key)
+        BH8_CUDA(ctx, cudaMemcpyAsync(out_key + fi * npx, d.d_key[b], npx, cudaMemcpyDeviceToHost, d.copy_stream));
+      if (out_steps)
+        BH8_CUDA(ctx, cudaMemcpyAsync(out_steps + fi * npx, d.d_steps[b], npx * 2, cudaMemcpyDeviceToHost,
+                                      d.copy_stream));
+      BH8_CUDA(ctx, cudaEventRecord(d.ev_copy_done[b], d.copy_stream));
+    }
+  }
+
+  double kernel_ms = 0;
+  for (int i = 0; i < n_active; ++i) {
+    Device& d = ctx->dev[i];
+    BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+    BH8_CUDA(ctx, cudaEventRecord(d.ev_t1, d.stream));
+  }
+  for (int i = 0; i < n_active; ++i) {
+    Device& d = ctx->dev[i];
+    BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+    BH8_CUDA(ctx, cudaStreamSynchronize(d.stream));
+    BH8_CUDA(ctx, cudaStreamSynchronize(d.copy_stream));
+    float ms = 0;
+    BH8_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_t0, d.ev_t1));
+    if (ms > kernel_ms) kernel_ms = ms;
+  }
+  if (stats) {
+    std::memset(stats, 0, sizeof *stats);
+    const int rc = read_stats(ctx, stats);
+    if (rc != BH8_OK) return rc;
+    stats->kernel_ms = kernel_ms;
+    stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+  }
+  return BH8_OK;
+}
+
+int bh8_frame_alloc(bh8_ctx* ctx, size_t bytes, void** d_ptr) {
+  if (!ctx || !d_ptr || bytes == 0) return BH8_EINVAL;
+  BH8_CUDA(ctx, cudaSetDevice(ctx->dev[0].ordinal));
+  void* p = nullptr;
+  BH8_CUDA(ctx, cudaMalloc(&p, bytes));
+  ctx->owned.push_back(p);
+  *d_ptr = p;
+  return BH8_OK;
+}
+
+int bh8_frame_free(bh8_ctx* ctx, void* d_ptr) {
+  if (!ctx) return BH8_EINVAL;
+  for (size_t i = 0; i < ctx->owned.size(); ++i)
+    if (ctx->owned[i] == d_ptr) {
+      BH8_CUDA(ctx, cudaSetDevice(ctx->dev[0].ordinal));
+      BH8_CUDA(ctx, cudaDeviceSynchronize());
+      BH8_CUDA(ctx, cudaFree(d_ptr));
+      ctx->owned.erase(ctx->owned.begin() + i);
+      return BH8_OK;
+    }
+  return fail(ctx, BH8_EINVAL, "pointer was not allocated by bh8_frame_alloc");
+}
+
+int bh8_ipc_export(bh8_ctx* ctx, void* d_ptr, uint8_t handle[64]) {
+  if (!ctx || !d_ptr || !handle) return BH8_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+  cudaIpcMemHandle_t h;
+  BH8_CUDA(ctx, cudaSetDevice(ctx->dev[0].ordinal));
+  BH8_CUDA(ctx, cudaIpcGetMemHandle(&h, d_ptr));
+  std::memcpy(handle, &h, 64);
+  return BH8_OK;
+}
+
+int bh8_ipc_import(bh8_ctx* ctx, const uint8_t handle[64], void** d_ptr) {
+  if (!ctx || !d_ptr || !handle) return BH8_EINVAL;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  BH8_CUDA(ctx, cudaSetDevice(ctx->dev[0].ordinal));
+  BH8_CUDA(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return BH8_OK;
+}
+
+int bh8_ipc_close(bh8_ctx* ctx, void* d_ptr) {
+  if (!ctx || !d_ptr) return BH8_EINVAL;
+  BH8_CUDA(ctx, cudaSetDevice(ctx->dev[0].ordinal));
+  BH8_CUDA(ctx, cudaStreamSynchronize(ctx->dev[0].stream));
+  BH8_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+  return BH8_OK;
+}
+
+int bh8_memcpy_d2h(bh8_ctx* ctx, void* host, const void* d_ptr, size_t bytes) {
+  if (!ctx || !host || !d_ptr) return BH8_EINVAL;
+  Device& d = ctx->dev[0];
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  BH8_CUDA(ctx, cudaMemcpyAsync(host, d_ptr, bytes, cudaMemcpyDeviceToHost, d.stream));
+  BH8_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return BH8_OK;
+}
+
+int bh8_memset_d(bh8_ctx* ctx, void* d_ptr, int value, size_t bytes) {
+  if (!ctx || !d_ptr) return BH8_EINVAL;
+  Device& d = ctx->dev[0];
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  BH8_CUDA(ctx, cudaMemsetAsync(d_ptr, value, bytes, d.stream));
+  return BH8_OK;
+}
+
+int bh8_host_alloc(void** p, size_t bytes) {
+  return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? BH8_OK : BH8_ENOMEM;
+}
+
+int bh8_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? BH8_OK : BH8_ECUDA; }
+
+int bh8_measure_fp64_peak(bh8_ctx* ctx, double* flops_per_s, double* seconds_run) {
+  if (!ctx || !flops_per_s) return BH8_EINVAL;
+  Device& d = ctx->dev[0];
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  cudaDeviceProp prop;
+  BH8_CUDA(ctx, cudaGetDeviceProperties(&prop, d.ordinal));
+  double* sink = nullptr;
+  BH8_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&sink), sizeof(double)));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  BH8_CUDA(ctx, cudaEventCreate(&e0));
+  BH8_CUDA(ctx, cudaEventCreate(&e1));
+  double best = 0, total_s = 0;
+  int iters = 2000;
+  for (int rep = 0; rep < 6; ++rep) {
+    BH8_CUDA(ctx, cudaEventRecord(e0, d.stream));
+    bh8::bh8_dfma_peak_kernel<<<blocks, threads, 0, d.stream>>>(sink, iters, 0.999999, 1e-7);
+    BH8_CUDA(ctx, cudaGetLastError());
+    BH8_CUDA(ctx, cudaEventRecord(e1, d.stream));
+    BH8_CUDA(ctx, cudaEventSynchronize(e1));
+    ctx->launches++;
+    float ms = 0;
+    BH8_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 64.0 * iters * static_cast<double>(blocks) * threads;
+    const double rate = flops / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+    total_s += ms * 1e-3;
+    if (ms < 20.0) iters *= 4;  // aim for tens of ms per launch
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *flops_per_s = best;
+  if (seconds_run) *seconds_run = total_s;
+  return BH8_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+"""Host-side mirror of the render call: Python over the C ABI of include/bh8.h (ctypes).
+
+`Renderer.render(snapshot)` is the batched replacement of the reference's inline pixel loop
+(include/blackhole/blackhole_solution_test.cc:161-308).  All pixels come from the CUDA kernels in
+libbh8.so; if the library or a CUDA device is missing this module raises -- there is no CPU path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .build import LIB, is_stale
+
+_lib = None
+
+
+class Bh8Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("bh8 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library(path=None):
+    """Load libbh8.so and declare the signatures of include/bh8.h."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB
+    if not os.path.exists(path):
+        raise RuntimeError(
+            "%s is missing: build it with `python -m blackhole_8_b200.build` (nvcc, sm_100a). "
+            "The renderer has no CPU fallback." % path)
+    L = C.CDLL(path)
+    vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+    sig = {
+        "bh8_abi_version": (i32, []),
+        "bh8_pixel_bytes": (C.c_size_t, [i32]),
+        "bh8_create": (i32, [C.POINTER(vp), C.POINTER(C.c_int), i32]),
+        "bh8_destroy": (None, [vp]),
+        "bh8_last_error": (C.c_char_p, [vp]),
+        "bh8_launch_count": (u64, [vp]),
+        "bh8_set_texture": (i32, [vp, i32, vp, i32, i32, C.c_size_t]),
+        "bh8_render": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), i32, C.POINTER(abi.Params),
+                             vp, vp, vp, vp, C.POINTER(abi.Stats)]),
+        "bh8_render_device": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params),
+                                    vp, vp, vp, vp]),
+        "bh8_sync": (i32, [vp]),
+        "bh8_timer_begin": (i32, [vp]),
+        "bh8_timer_end_ms": (i32, [vp, C.POINTER(C.c_double)]),
+        "bh8_read_stats": (i32, [vp, C.POINTER(abi.Stats)]),
+        "bh8_frame_alloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
+        "bh8_frame_free": (i32, [vp, vp]),
+        "bh8_ipc_export": (i32, [vp, vp, vp]),
+        "bh8_ipc_import": (i32, [vp, vp, C.POINTER(vp)]),
+        "bh8_ipc_close": (i32, [vp, vp]),
+        "bh8_memcpy_d2h": (i32, [vp, vp, vp, C.c_size_t]),
+        "bh8_memset_d": (i32, [vp, vp, i32, C.c_size_t]),
+        "bh8_host_alloc": (i32, [C.POINTER(vp), C.c_size_t]),
+        "bh8_host_free": (i32, [vp]),
+        "bh8_measure_fp64_peak": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    if L.bh8_abi_version() != abi.ABI_VERSION:
+        raise RuntimeError("libbh8.so ABI %d != python mirror %d" % (L.bh8_abi_version(), abi.ABI_VERSION))
+    if path == LIB:
+        _lib = L
+    return L
+
+
+class PinnedBuffer:
+    """cudaHostAlloc'ed host memory viewed as a numpy array."""
+
+    def __init__(self, lib, shape, dtype):
+        self._lib = lib
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        rc = lib.bh8_host_alloc(C.byref(p), max(1, self.nbytes))
+        if rc != 0:
+            raise Bh8Error(rc, "cudaHostAlloc failed")
+        self.ptr = p.value
+        buf = (C.c_uint8 * max(1, self.nbytes)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.bh8_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+
+class Renderer:
+    """One bh8 context (one or more CUDA devices of this process)."""
+
+    def __init__(self, devices=(0,)):
+        self.lib = load_library()
+        self._ctx = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        rc = self.lib.bh8_create(C.byref(self._ctx), devs, len(devices))
+        if rc != 0:
+            raise Bh8Error(rc, (self.lib.bh8_last_error(None) or b"").decode())
+        self.devices = tuple(devices)
+        self._textures = {}
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise Bh8Error(rc, (self.lib.bh8_last_error(self._ctx) or b"").decode())
+
+    def close(self):
+        if self._ctx:
+            self.lib.bh8_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def launches(self):
+        return int(self.lib.bh8_launch_count(self._ctx))
+
+    # -- scene inputs ----------------------------------------------------------------------------
+    def set_texture(self, slot, bgr):
+        """bgr: (rows, cols, 3) uint8, the decoded Material::texture_ (BGR)."""
+        bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+        assert bgr.ndim == 3 and bgr.shape[2] == 3
+        self._check(self.lib.bh8_set_texture(self._ctx, slot, bgr.ctypes.data_as(C.c_void_p), bgr.shape[0],
+                                             bgr.shape[1], bgr.strides[0]))
+        self._textures[slot] = bgr.shape[:2]
+
+    def set_textures(self, snapshot, loader):
+        for slot, name in enumerate(snapshot.textures):
+            self.set_texture(slot, loader(name))
+
+    # -- host-buffer path (what a user calls) ------------------------------------------------------
+    def render(self, snapshots, nstep=None, pixel_format=abi.PIXEL_RGBA8, want_maps=False, flags=0,
+               stats=False, out=None, stripe_rows=0):
+        """Render one snapshot or a list of them (same size) -> dict(pixels[, cls, key, steps, stats]).
+
+        pixels: (n, H, W, bpp) uint8 in host memory.  Pass `out` (a dict of pre-allocated, ideally
+        pinned arrays) to avoid allocations in a timed loop."""
+        single = isinstance(snapshots, abi.SceneSnapshot)
+        snaps = [snapshots] if single else list(snapshots)
+        n = len(snaps)
+        h, w = snaps[0].height, snaps[0].width
+        bpp = abi.pixel_bytes(pixel_format)
+        scenes = (abi.Scene * n)(*[s.scene for s in snaps])
+        cams = (abi.Camera * n)(*[s.camera for s in snaps])
+        prm = abi.Params(nstep or snaps[0].nstep, pixel_format, flags, stripe_rows, 0, 0)
+        res = out if out is not None else {}
+        if "pixels" not in res:
+            res["pixels"] = np.empty((n, h, w, bpp), np.uint8)
+        if want_maps:
+            res.setdefault("cls", np.empty((n, h, w), np.uint8))
+            res.setdefault("key", np.empty((n, h, w), np.int8))
+            res.setdefault("steps", np.empty((n, h, w), np.uint16))
+        st = abi.Stats() if stats else None
+
+        def ptr(name):
+            a = res.get(name)
+            return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+        self._check(self.lib.bh8_render(self._ctx, scenes, cams, n, C.byref(prm), ptr("pixels"), ptr("cls"),
+                                        ptr("key"), ptr("steps"), C.byref(st) if stats else None))
+        if stats:
+            res["stats"] = st
+        return res
+
+    # -- device-resident path --------------------------------------------------------------------------
+    def frame_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.lib.bh8_frame_alloc(self._ctx, nbytes, C.byref(p)))
+        return p.value
+
+    def frame_free(self, ptr):
+        self._check(self.lib.bh8_frame_free(self._ctx, C.c_void_p(ptr)))
+
+    def render_device(self, snap, d_pixels, d_cls=None, d_key=None, d_steps=None, nstep=None,
+                      pixel_format=abi.PIXEL_RGBA8, flags=0, stripe_rows=0, shard_index=0, shard_count=0):
+        prm = abi.Params(nstep or snap.nstep, pixel_format, flags, stripe_rows, shard_index, shard_count)
+        self._check(self.lib.bh8_render_device(self._ctx, C.byref(snap.scene), C.byref(snap.camera), C.byref(prm),
+                                               C.c_void_p(d_pixels), C.c_void_p(d_cls), C.c_void_p(d_key),
+                                               C.c_void_p(d_steps)))
+
+    def sync(self):
+        self._check(self.lib.bh8_sync(self._ctx))
+
+    def timer_begin(self):
+        self._check(self.lib.bh8_timer_begin(self._ctx))
+
+    def timer_end_ms(self):
+        ms = C.c_double()
+        self._check(self.lib.bh8_timer_end_ms(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def read_stats(self):
+        st = abi.Stats()
+        self._check(self.lib.bh8_read_stats(self._ctx, C.byref(st)))
+        return st
+
+    def memcpy_d2h(self, host_array, d_ptr):
+        self._check(self.lib.bh8_memcpy_d2h(self._ctx, host_array.ctypes.data_as(C.c_void_p), C.c_void_p(d_ptr),
+                                            host_array.nbytes))
+
+    def memset_d(self, d_ptr, value, nbytes):
+        self._check(self.lib.bh8_memset_d(self._ctx, C.c_void_p(d_ptr), value, nbytes))
+
+    def ipc_export(self, d_ptr):
+        h = (C.c_uint8 * 64)()
+        self._check(self.lib.bh8_ipc_export(self._ctx, C.c_void_p(d_ptr), h))
+        return bytes(h)
+
+    def ipc_import(self, handle):
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self.lib.bh8_ipc_import(self._ctx, h, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, d_ptr):
+        self._check(self.lib.bh8_ipc_close(self._ctx, C.c_void_p(d_ptr)))
+
+    def pinned(self, shape, dtype=np.uint8):
+        return PinnedBuffer(self.lib, shape, dtype)
+
+    def measure_fp64_peak(self):
+        f, s = C.c_double(), C.c_double()
+        self._check(self.lib.bh8_measure_fp64_peak(self._ctx, C.byref(f), C.byref(s)))
+        return f.value, s.value

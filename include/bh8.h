@@ -181,6 +181,9 @@ int bh8_ipc_export(bh8_ctx* ctx, void* d_ptr, uint8_t handle[64]);
 int bh8_ipc_import(bh8_ctx* ctx, const uint8_t handle[64], void** d_ptr);
 int bh8_ipc_close(bh8_ctx* ctx, void* d_ptr);
 int bh8_memcpy_d2h(bh8_ctx* ctx, void* host, const void* d_ptr, size_t bytes);
+/* Pinned host memory (cudaHostAlloc) so the frame read-back of bh8_render() is a true async DMA. */
+int bh8_host_alloc(void** p, size_t bytes);
+int bh8_host_free(void* p);
 int bh8_memset_d(bh8_ctx* ctx, void* d_ptr, int value, size_t bytes);
 
 /* FP64 pipe peak: runs a dependent-free DFMA chain on every SM of device 0 and reports the

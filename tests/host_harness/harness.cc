@@ -1,0 +1,74 @@
+// TEST-ONLY harness: runs the per-ray code of blackhole_8_b200/csrc/bh8_ray.cuh (the exact source
+// the CUDA kernel inlines) on the CPU, pixel by pixel, so the algorithmic restructuring (closed-form
+// ray setup, phi-crossing / distance / horizon filters, acos-free texture index) can be checked
+// against the oracle without a GPU.  It is compiled only by tests/test_ray_math_host.py into
+// tests/host_harness/_build/; the product library never contains or calls it -- there is no CPU
+// rendering path in libbh8.so.
+#include <cstdint>
+#include <cstring>
+
+#include "bh8_ray.cuh"
+
+struct HarnessTexture {
+  const uint8_t* bgr;
+  int32_t rows, cols;
+};
+
+struct HostFetch {
+  const HarnessTexture* tex;
+  uint32_t operator()(int slot, int col, int row) const {
+    const uint8_t* p = tex[slot].bgr + (static_cast<size_t>(row) * tex[slot].cols + col) * 3;
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+  }
+};
+
+extern "C" int bh8_harness_render(const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
+                                  const HarnessTexture* textures, int n_textures, uint8_t* out_bgr,
+                                  uint8_t* out_class, int8_t* out_key, uint16_t* out_steps, char* err) {
+  int rows[BH8_MAX_TEXTURES] = {0}, cols[BH8_MAX_TEXTURES] = {0};
+  for (int i = 0; i < n_textures && i < BH8_MAX_TEXTURES; ++i) {
+    rows[i] = textures[i].rows;
+    cols[i] = textures[i].cols;
+  }
+  Bh8Frame f;
+  const int rc = bh8_build_frame(scene, cam, prm, rows, cols, &f, err);
+  if (rc != BH8_OK) return rc;
+  const HostFetch fetch{textures};
+  for (int y = 0; y < f.height; ++y) {
+    for (int x = 0; x < f.width; ++x) {
+      bh8::Ray r;
+      bh8::Hit h;
+      h.obj = -1;
+      bool alive = true;
+      bh8::ray_setup(f, x, y, r);
+      if (r.flags & bh8::kDegenerate) {
+        bh8::ray_degenerate(f, r, h);
+        alive = false;
+      }
+      const int nsafe = f.nstep - 1;
+      for (int i = 0; i < f.nstep && alive; ++i)
+        if (bh8::ray_step(f, r, i < nsafe ? r.du : r.du * 0.9, h)) alive = false;
+      if (alive && (r.flags & bh8::kCaptured)) {
+        bh8::ray_chord(f, r, h);
+        alive = false;
+      }
+      for (int i = 0; i < nsafe && alive; ++i)
+        if (bh8::ray_step(f, r, -r.du, h)) alive = false;
+      uint32_t bgr = 0, oob = 0;
+      int cls = BH8_CLASS_BACKGROUND, key = -1;
+      if (h.obj >= 0) {
+        bgr = bh8::shade(f, h.obj, h.p, fetch, &oob);
+        cls = f.obj[h.obj].cls;
+        key = f.obj[h.obj].key;
+      }
+      const size_t i = static_cast<size_t>(y) * f.width + x;
+      out_bgr[3 * i] = bgr & 255;
+      out_bgr[3 * i + 1] = (bgr >> 8) & 255;
+      out_bgr[3 * i + 2] = (bgr >> 16) & 255;
+      out_class[i] = (uint8_t)cls;
+      out_key[i] = (int8_t)key;
+      out_steps[i] = (uint16_t)r.steps;
+    }
+  }
+  return BH8_OK;
+}

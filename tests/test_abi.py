@@ -1,0 +1,62 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/bh8.h declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from blackhole_8_b200 import abi
+from blackhole_8_b200.build import LIB, build
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build()
+    from blackhole_8_b200.renderer import load_library
+    return load_library()
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "bh8.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bh8_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_abi_version_and_struct_sizes(lib):
+    assert lib.bh8_abi_version() == abi.ABI_VERSION
+    assert C.sizeof(abi.Camera) == 13 * 8 + 8
+    assert C.sizeof(abi.Object) == 16 + (15 + 9 + 4) * 8
+    assert C.sizeof(abi.Scene) == 16
+    assert C.sizeof(abi.Params) == 24
+    assert C.sizeof(abi.Stats) == 9 * 8
+    assert lib.bh8_pixel_bytes(abi.PIXEL_BGR8) == 3 and lib.bh8_pixel_bytes(abi.PIXEL_RGBA8) == 4
+
+
+def test_no_cpu_fallback_without_a_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    ctx = C.c_void_p()
+    rc = lib.bh8_create(C.byref(ctx), None, 1)
+    assert rc == abi.ENODEVICE and not ctx.value
+    assert b"no CPU fallback" in lib.bh8_last_error(None)
+
+
+def test_product_package_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "blackhole_8_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                text = open(os.path.join(dirpath, f)).read()
+                bad = re.findall(r"import\s+\S*oracle|from\s+\S*oracle|libbh8_oracle|bh8_oracle_|"
+                                 r"#include\s+\"[^\"]*oracle|CDLL\([^)]*oracle", text)
+                assert not bad, (os.path.join(dirpath, f), bad)

@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Snapshot the 240 frames of BASELINE configs[3] (camera fly-through) with the REFERENCE's classes.
+
+oracle/_ref/ref_render --cfg 3 --frame k replays the reference's own Camera::MoveX/RotateZ/MoveY and
+Annulus::RotateZ calls (object.h:58-88) k times and dumps the resulting state; this tool stores, per
+frame, the camera and the vertices of every object in tests/golden/cfg3_flythrough.json (doubles as
+%.17g).  Runs only in the build container.
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_render")
+
+
+def main():
+    if not os.path.exists(REF):
+        sys.exit("oracle/_ref/ref_render missing: run `make -C oracle ref`")
+    frames = []
+    base = None
+    for k in range(240):
+        out = subprocess.run([REF, "--cfg", "3", "--width", "1920", "--height", "1080", "--frame", str(k),
+                              "--snapshot-only", "--texdir", os.path.join(ROOT, "build", "textures")],
+                             check=True, capture_output=True, text=True).stdout
+        d = json.loads(out)
+        if base is None:
+            base = d
+        frames.append({"camera": {k2: d["camera"][k2] for k2 in ("pos", "vx", "vy", "vz")},
+                       "v": [o["v"] for o in d["objects"]]})
+    base.pop("run", None)
+    with open(os.path.join(ROOT, "tests", "golden", "cfg3_flythrough.json"), "w") as f:
+        json.dump({"base": base, "frames": frames}, f)
+    print("wrote %d frames" % len(frames))
+
+
+if __name__ == "__main__":
+    main()
