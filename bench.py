@@ -56,11 +56,11 @@ def load_texture(name):
 
 def flythrough_snapshots(n_frames=240):
     """Frames of BASELINE configs[3]: the per-frame camera / disc states the reference's own classes
-    produce when its frame loop is replayed (tools/make_flythrough.py -> tests/golden/cfg3_flythrough.json;
+    produce when its frame loop is replayed (tools/make_flythrough.py -> tests/golden/states/cfg3_flythrough.json;
     'w' MoveX(+10) for frames 0-119, then 'L' RotateZ(pi/180) + 'd' MoveY(+10), disc RotateZ(pi/180)
     every frame: blackhole_solution_test.cc:346-407)."""
     from blackhole_8_b200 import abi
-    with open(os.path.join(ROOT, "tests", "golden", "cfg3_flythrough.json")) as f:
+    with open(os.path.join(ROOT, "tests", "golden", "states", "cfg3_flythrough.json")) as f:
         fly = json.load(f)
     out = []
     for fr in fly["frames"][:n_frames]:
@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-compaction", action="store_true")
+    ap.add_argument("--no-batching", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,7 +215,7 @@ def main():
     rays = H * W
     r = Renderer((local_rank,))
     r.set_textures(base, load_texture)
-    flags = abi.FLAG_NO_COMPACTION if args.no_compaction else 0
+    flags = abi.FLAG_NO_BATCHING if args.no_batching else 0
 
     # frames this rank renders: N == 1 -> the configs[1] frame every step; N > 1 -> fly-through frames
     if world > 1:
@@ -345,7 +345,7 @@ def main():
                    "class_mix": {"background": st.class_count[0] / st.rays, "horizon": st.class_count[1] / st.rays,
                                  "disc": st.class_count[2] / st.rays, "object": st.class_count[3] / st.rays},
                    "l2": "flushed between steps by a 256 MiB memset outside the per-step CUDA-event pair",
-                   "compaction": not args.no_compaction},
+                   "batched_resolve": not args.no_batching},
         "frames_per_s": world * 1e3 / ms_per_step,
         "gsteps_per_s": st.steps * world / (ms_per_step * 1e-3) / 1e9,
         "wall_s_timed_region": wall_s,

@@ -16,7 +16,7 @@ KIND_BLACKHOLE, KIND_ANNULUS, KIND_RECTANGLE, KIND_INFINITE_PLANE = 0, 1, 2, 3
 CLASS_BACKGROUND, CLASS_HORIZON, CLASS_DISC, CLASS_OBJECT = 0, 1, 2, 3
 PATTERN_BLACK, PATTERN_CHESS = 0, 1
 PIXEL_RGBA8, PIXEL_BGRA8, PIXEL_BGR8 = 0, 1, 2
-FLAG_STATS, FLAG_NO_COMPACTION = 1, 2
+FLAG_STATS, FLAG_NO_BATCHING = 1, 2
 
 EINVAL, EUNSUPPORTED, ECUDA, ENOMEM, ENODEVICE = -1, -2, -3, -4, -5
 

@@ -32,17 +32,19 @@ def is_stale():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force=False, verbose=False):
-    """Compile blackhole_8_b200/csrc/bh8_lib.cu -> blackhole_8_b200/libbh8.so."""
-    if not force and not is_stale():
+def build(force=False, verbose=False, out=None, defines=()):
+    """Compile blackhole_8_b200/csrc/bh8_lib.cu -> blackhole_8_b200/libbh8.so (or `out`, with extra
+    -D defines, for tuning variants selected at run time through $BH8_LIB_PATH)."""
+    if out is None and not force and not is_stale():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + ["-I" + os.path.join(ROOT, "include"), "-I" + SRC,
-                                   "-o", LIB, os.path.join(SRC, "bh8_lib.cu")]
+    out = out or LIB
+    cmd = [nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + \
+        ["-I" + os.path.join(ROOT, "include"), "-I" + SRC, "-o", out, os.path.join(SRC, "bh8_lib.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     subprocess.run(cmd, check=True)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -24,6 +24,7 @@ struct Bh8Obj {
   double p0[3];   // point of the plane: Annulus center() / Rectangle vertex()[1] / plane position(); BH centre
   double d;       // n . p0
   double c_bh;    // n . (bh_pos - p0): signed distance of the black hole from the plane (0 => central)
+  double nF;      // n . Fhat (Fhat = F/|F|): the plane normal's component along the camera direction
   double e1[3], e3[3], e1e1, e3e3;  // Rectangle edges vertex()[2]-[1], vertex()[4]-[1]
   double r_in, r_out;               // Annulus radii
   double t0[3], s1[3];              // texture frame (Rectangle::color): origin vertex()[1], s1 = [2]-[1]
@@ -39,6 +40,7 @@ struct Bh8Frame {
   int32_t width, height;
   // black hole (blackhole_solution.h:24-57)
   double bh[3], F[3];     // F = camera.focus() - blackhole.position()
+  double Fhat[3];         // F / |F|
   double FF;              // F . F
   double mass, two_m, b_c2 /* b_c^2 */, inv3m, R, R2;
   double r0, u0;          // |F| and 1/|F|: convertedCameraFocus has the length of F
@@ -50,10 +52,15 @@ struct Bh8Frame {
   // conservative filters (see bh8_ray.cuh)
   double u_gate;        // non-central planes can only be crossed while min(u) <= u_gate
   double u_horizon;     // horizon sphere cannot be reached while u <= u_horizon and |dphi| <= 1
-  uint32_t cam_mask;    // sign bits of n.cam - d per object (state of the first segment's start)
-  uint32_t noncentral_mask;  // objects handled by the sign-mask filter
+  uint32_t noncentral_mask;  // objects handled by the side-sign filter
   uint32_t central_mask;     // objects handled by the phi-crossing filter
   int32_t first_resolve;     // 1: always resolve the first segment exactly (camera too close / in a plane)
+  int32_t n_nc;              // number of non-central planes (<= BH8_MAX_OBJECTS)
+  int32_t nc_obj[BH8_MAX_OBJECTS];  // their object indices, in scene order
+  float nc_nF[BH8_MAX_OBJECTS];     // float(n . Fhat)
+  float nc_c[BH8_MAX_OBJECTS];      // float(c_bh)
+  uint32_t nc_cam_bits;      // side of the camera w.r.t. non-central plane j: bit j = positive, bit 16+j = negative
+  int32_t resolve_wait;      // warp iterations a pending exact test may wait for company (batching window)
   // output
   int32_t pixel_format, stripe_rows, shard_index, shard_count;
   uint32_t flags;
@@ -113,6 +120,8 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
   f->height = cam->height;
   bh8h_sub(f->F, f->cam, f->bh);
   f->FF = bh8h_dot(f->F, f->F);
+  for (int i = 0; i < 3; ++i) f->Fhat[i] = f->F[i] / sqrt(f->FF);
+  f->resolve_wait = 2;
   f->mass = bho->mass;
   f->two_m = 2.0 * bho->mass;
   const double b_c = 3.0 * sqrt(3.0) * bho->mass;  // blackhole_solution.h:25
@@ -204,6 +213,7 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
       q->c_bh = bh8h_dot(q->n, w);
     }
     q->central = (q->c_bh == 0.0);
+    q->nF = bh8h_dot(q->n, f->Fhat);
     if (o->kind == BH8_KIND_ANNULUS || o->kind == BH8_KIND_RECTANGLE) {
       double s2[3];
       for (int i = 0; i < 3; ++i) q->t0[i] = o->v[1][i];  // vector_object.h:164-166
@@ -221,14 +231,21 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
         q->kh = q->tex_rows / sqrt(bh8h_dot(s2, s2));
       }
     }
-    const double side_cam = bh8h_dot(q->n, f->cam) - q->d;
-    if (side_cam < 0) f->cam_mask |= 1u << k;
+    double wc[3];
+    bh8h_sub(wc, f->cam, q->p0);
+    const double side_cam = bh8h_dot(q->n, wc);
     if (side_cam == 0) f->first_resolve = 1;
     if (q->central) {
       f->central_mask |= 1u << k;
       f->n_central++;
     } else {
+      const int j = f->n_nc++;
       f->noncentral_mask |= 1u << k;
+      f->nc_obj[j] = k;
+      f->nc_nF[j] = (float)q->nF;
+      f->nc_c[j] = (float)q->c_bh;
+      if (side_cam > 0) f->nc_cam_bits |= 1u << j;
+      if (side_cam < 0) f->nc_cam_bits |= 1u << (16 + j);
       if (fabs(q->c_bh) < min_dist) min_dist = fabs(q->c_bh);
     }
   }

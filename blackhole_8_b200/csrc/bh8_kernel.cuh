@@ -3,17 +3,19 @@
 // Replaces the pixel loop of blackhole_solution_test.cc:162-298 (ray setup, inbound steps, 0.9-step,
 // captured chord, outbound steps, colour, frame store) for a whole frame or a set of row stripes.
 //
-// CTA schedule
-//   A  every thread sets up its ray and runs the inbound leg (nstep-1 steps of +du, one of +0.9du).
-//      A warp is an 8x4-pixel patch (neighbouring rays end at neighbouring steps); the leg loop
-//      leaves as soon as __any_sync() reports no live lane, so finished patches cost nothing.
-//   B  captured rays (b < b_c) take their straight chord to the centre and finish.
-//   C  mid-ray compaction: the survivors' states are packed through shared memory with
-//      ballot/popc ranks so the outbound leg runs in dense warps -- rays that ended on the way in
-//      (disc hits, the horizon) no longer hold lanes of a half-empty warp.
-//   D  outbound leg (nstep-1 steps of -du) on the packed rays; hits go back to the pixel's slot.
-//   E  every thread colours its own pixel slot (texture object fetch / chess / black) into a shared
-//      RGBA tile, which leaves as 16-byte coalesced stores (4 pixels per store, 128 B per row).
+// Warp schedule.  A warp is an 8x4-pixel patch, so neighbouring rays end at neighbouring steps.
+// Every lane walks its own ray through ONE loop whose body is the lean geodesic update
+// (ray_advance: ~12 FP64 instructions); the step index is per-lane state, so lanes may drift apart.
+// A lane whose segment needs the exact object test (a plane crossing, a possible horizon hit) does
+// not run it on the spot -- that would serialise the warp once per distinct hit step -- but parks
+// (`pend`) while the other lanes keep stepping.  __ballot_sync() tells the warp who is parked and
+// who still runs; the exact tests (ray_resolve: sincos, 1/u, every object's Collide()) are executed
+// together once no lane is left running or the oldest has waited `resolve_wait` iterations, so the
+// expensive divergent section runs for many lanes at once.  Rays that end (hit, captured, escaped to
+// r ~ r0) drop out of the ballots; the loop leaves when __any_sync() finds no live lane, so a patch
+// that has finished early does not wait for anything.
+// Colour (texture object fetch / chess / black) goes into a shared RGBA tile that leaves as 16-byte
+// coalesced stores: 4 pixels per store, 128 B per tile row.
 #ifndef BH8_KERNEL_CUH_
 #define BH8_KERNEL_CUH_
 
@@ -26,8 +28,10 @@ namespace bh8 {
 constexpr int kTileW = 32;
 constexpr int kTileH = 8;
 constexpr int kThreads = kTileW * kTileH;
-constexpr int kWarps = kThreads / 32;
-constexpr int kStateDoubles = 12;
+constexpr int kMaxFilterPlanes = 4;
+#ifndef BH8_MIN_BLOCKS
+#define BH8_MIN_BLOCKS 3  // CTAs per SM the register allocation is sized for
+#endif
 
 struct Bh8Tex {
   unsigned long long obj[BH8_MAX_TEXTURES];
@@ -42,20 +46,6 @@ struct Bh8Out {
   int32_t vec_ok;             // 16-byte row stores are legal (width % 4 == 0, base 16-byte aligned)
 };
 
-struct TileShared {
-  double hp[3][kThreads];              // hit point per pixel slot
-  double st[kStateDoubles][kThreads];  // packed ray states (compaction)
-  uint32_t st_mask[kThreads];
-  uint32_t rgba[kThreads];
-  uint16_t st_pix[kThreads];
-  uint16_t st_meta[kThreads];  // flags
-  uint16_t st_steps[kThreads];
-  uint16_t steps[kThreads];
-  int8_t hobj[kThreads];
-  int32_t warp_cnt[kWarps];
-  unsigned long long red[7];
-};
-
 struct DeviceFetch {
   const Bh8Tex& tex;
   __device__ __forceinline__ uint32_t operator()(int slot, int col, int row) const {
@@ -64,20 +54,11 @@ struct DeviceFetch {
   }
 };
 
-__device__ __forceinline__ void record_hit(TileShared& sh, int slot, const Hit& h, int steps) {
-  sh.hobj[slot] = (int8_t)h.obj;
-  sh.steps[slot] = (uint16_t)steps;
-  if (h.obj >= 0) {
-    sh.hp[0][slot] = h.p[0];
-    sh.hp[1][slot] = h.p[1];
-    sh.hp[2][slot] = h.p[2];
-  }
-}
-
-template <bool kCompact>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int NN>
+__global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
 bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
-  __shared__ TileShared sh;
+  __shared__ __align__(16) uint32_t sh_rgba[kThreads];
+  __shared__ unsigned long long sh_red[7];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
 
@@ -101,122 +82,76 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
   const int x = x0 + px, y = y0 + py;
   const bool inside = x < f.width && y < f.height;
 
-  // ---- A: setup + inbound leg ------------------------------------------------------------------
-  Ray r;
+  // ---- trace ----------------------------------------------------------------------------------
+  Ray<NN> r;
+  Cand c;
   Hit h;
   h.obj = -1;
-  bool alive = inside;
-  r.steps = 0;
-  r.flags = 0;
+  bool alive = inside, pend = false, chord = false;
+  int steps = 0;
+  r.i = 0;
   if (inside) {
     ray_setup(f, x, y, r);
     if (r.flags & kDegenerate) {
-      ray_degenerate(f, r, h);
+      ray_degenerate(f, h);
+      steps = 1;
       alive = false;
     }
   }
-  const int nsafe = f.nstep - 1;
-  for (int i = 0; i < f.nstep; ++i) {
-    if (!__any_sync(0xffffffffu, alive)) break;
-    if (alive) {
-      const double delta = (i < nsafe) ? r.du : r.du * 0.9;  // :218 / :241
-      if (ray_step(f, r, delta, h)) alive = false;
+  const int n_total = 2 * f.nstep - 1;
+  int waited = 0;
+  while (__any_sync(0xffffffffu, alive)) {
+    bool stepped = false;
+    if (alive && !pend) {
+      if (ray_advance(f, r, c)) {
+        pend = true;
+      } else {
+        ray_commit(f, r, c);
+        stepped = true;
+      }
     }
-  }
-  // ---- B: captured rays ------------------------------------------------------------------------
-  if (alive && (r.flags & kCaptured)) {
-    ray_chord(f, r, h);
-    alive = false;
+    const unsigned pending = __ballot_sync(0xffffffffu, pend);
+    if (pending) {
+      const unsigned running = __ballot_sync(0xffffffffu, alive && !pend);
+      if (running == 0u || ++waited > f.resolve_wait) {
+        waited = 0;
+        if (pend) {
+          pend = false;
+          if (chord) {  // captured ray: straight chord to the centre, :264-272
+            ray_chord(f, r, h);
+            steps = r.i;
+            alive = false;
+          } else if (ray_resolve(f, r, c, h)) {
+            steps = r.i + 1;
+            alive = false;
+          } else {
+            stepped = true;
+          }
+        }
+      }
+    }
+    if (stepped) {
+      if (r.i == f.nstep && (r.flags & kCaptured)) {
+        pend = true;
+        chord = true;
+      } else if (r.i >= n_total) {  // ray ends near r0 without a hit: pixel stays 0
+        steps = r.i;
+        alive = false;
+      }
+    }
   }
 
-  if (!kCompact) {
-    // ---- D (in place) ---------------------------------------------------------------------------
-    for (int i = 0; i < nsafe; ++i) {
-      if (!__any_sync(0xffffffffu, alive)) break;
-      if (alive) {
-        if (ray_step(f, r, -r.du, h)) alive = false;  // :275
-      }
-    }
-    record_hit(sh, slot, h, r.steps);
-  } else {
-    // ---- C: pack survivors -----------------------------------------------------------------------
-    if (!alive) record_hit(sh, slot, h, r.steps);
-    const unsigned bal = __ballot_sync(0xffffffffu, alive);
-    if (lane == 0) sh.warp_cnt[warp] = __popc(bal);
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      const int c = sh.warp_cnt[w];
-      if (w < warp) base += c;
-      total += c;
-    }
-    if (alive) {
-      const int dst = base + __popc(bal & ((1u << lane) - 1u));
-      sh.st[0][dst] = r.u;
-      sh.st[1][dst] = r.phi;
-      sh.st[2][dst] = r.dphi_prev;
-      sh.st[3][dst] = r.du;
-      sh.st[4][dst] = r.binv2;
-      sh.st[5][dst] = r.phi_next;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        sh.st[6 + i][dst] = r.yv[i];
-        sh.st[9 + i][dst] = r.xv[i];
-      }
-      sh.st_mask[dst] = r.mask;
-      sh.st_pix[dst] = (uint16_t)slot;
-      sh.st_meta[dst] = (uint16_t)r.flags;
-      sh.st_steps[dst] = (uint16_t)r.steps;
-    }
-    __syncthreads();
-    // ---- D: outbound leg on packed rays ------------------------------------------------------------
-    alive = tid < total;
-    int pix = 0;
-    if (alive) {
-      r.u = sh.st[0][tid];
-      r.phi = sh.st[1][tid];
-      r.dphi_prev = sh.st[2][tid];
-      r.du = sh.st[3][tid];
-      r.binv2 = sh.st[4][tid];
-      r.phi_next = sh.st[5][tid];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        r.yv[i] = sh.st[6 + i][tid];
-        r.xv[i] = sh.st[9 + i][tid];
-      }
-      r.mask = sh.st_mask[tid];
-      pix = sh.st_pix[tid];
-      r.flags = sh.st_meta[tid];
-      r.steps = sh.st_steps[tid];
-      h.obj = -1;
-    }
-    const bool mine = alive;
-    for (int i = 0; i < nsafe; ++i) {
-      if (!__any_sync(0xffffffffu, alive)) break;
-      if (alive) {
-        if (ray_step(f, r, -r.du, h)) alive = false;  // :275
-      }
-    }
-    if (mine) record_hit(sh, pix, h, r.steps);
-  }
-  __syncthreads();
-
-  // ---- E: colour own slot (slot == tid in row-major tile order) ----------------------------------
-  const int cx = x0 + (tid & 31), cy = y0 + (tid >> 5);
-  const bool cin = cx < f.width && cy < f.height;
-  const int ho = sh.hobj[tid];
+  // ---- colour ------------------------------------------------------------------------------------
   uint32_t bgr = 0, oob = 0;
   int cls = BH8_CLASS_BACKGROUND, key = -1;
-  if (cin && ho >= 0) {
-    const double p[3] = {sh.hp[0][tid], sh.hp[1][tid], sh.hp[2][tid]};
-    bgr = shade(f, ho, p, DeviceFetch{tex}, &oob);
-    cls = f.obj[ho].cls;
-    key = f.obj[ho].key;
+  if (inside && h.obj >= 0) {
+    bgr = shade(f, h.obj, h.p, DeviceFetch{tex}, &oob);
+    cls = f.obj[h.obj].cls;
+    key = f.obj[h.obj].key;
   }
-  const size_t gi = (size_t)cy * f.width + cx;
+  const size_t gi = (size_t)y * f.width + x;
   if (f.pixel_format == BH8_PIXEL_BGR8) {
-    if (cin) {
+    if (inside) {
       uint8_t* d = out.pixels + gi * 3;
       d[0] = (uint8_t)bgr;
       d[1] = (uint8_t)(bgr >> 8);
@@ -227,43 +162,43 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
                              ? (bgr | 0xFF000000u)
                              : (((bgr >> 16) & 0xFFu) | (bgr & 0xFF00u) | ((bgr & 0xFFu) << 16) | 0xFF000000u);
     if (out.vec_ok) {
-      sh.rgba[tid] = px4;
+      sh_rgba[slot] = px4;
       __syncthreads();
       if (tid < kThreads / 4) {
         const int row = tid >> 3, col = (tid & 7) * 4;
         if (x0 + col < f.width && y0 + row < f.height) {
-          const uint4 v = *reinterpret_cast<const uint4*>(&sh.rgba[row * kTileW + col]);
+          const uint4 v = *reinterpret_cast<const uint4*>(&sh_rgba[row * kTileW + col]);
           *reinterpret_cast<uint4*>(out.pixels + ((size_t)(y0 + row) * f.width + x0 + col) * 4) = v;
         }
       }
-    } else if (cin) {
+    } else if (inside) {
       reinterpret_cast<uint32_t*>(out.pixels)[gi] = px4;
     }
   }
-  if (cin) {
+  if (inside) {
     if (out.cls) out.cls[gi] = (uint8_t)cls;
     if (out.key) out.key[gi] = (int8_t)key;
-    if (out.steps) out.steps[gi] = sh.steps[tid];
+    if (out.steps) out.steps[gi] = (uint16_t)steps;
   }
 
   // ---- optional counters ----------------------------------------------------------------------------
   if (f.flags & BH8_FLAG_STATS) {
-    if (tid < 7) sh.red[tid] = 0ull;
+    if (tid < 7) sh_red[tid] = 0ull;
     __syncthreads();
     unsigned long long v[7];
-    v[0] = cin ? 1ull : 0ull;
-    v[1] = cin ? (unsigned long long)sh.steps[tid] : 0ull;
-    for (int c = 0; c < 4; ++c) v[2 + c] = (cin && cls == c) ? 1ull : 0ull;
+    v[0] = inside ? 1ull : 0ull;
+    v[1] = inside ? (unsigned long long)steps : 0ull;
+    for (int k = 0; k < 4; ++k) v[2 + k] = (inside && cls == k) ? 1ull : 0ull;
     v[6] = oob;
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
       unsigned long long s = v[k];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0 && s) atomicAdd(&sh.red[k], s);
+      if (lane == 0 && s) atomicAdd(&sh_red[k], s);
     }
     __syncthreads();
-    if (tid < 7 && sh.red[tid]) atomicAdd(&out.stats[tid], sh.red[tid]);
+    if (tid < 7 && sh_red[tid]) atomicAdd(&out.stats[tid], sh_red[tid]);
   }
 }
 

@@ -7,6 +7,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -110,10 +111,18 @@ int launch_frame(bh8_ctx* ctx, Device& d, const bh8_scene* scene, const bh8_came
   out.vec_ok = (f.width % 4 == 0) && (reinterpret_cast<uintptr_t>(d_pixels) % 16 == 0) &&
                f.pixel_format != BH8_PIXEL_BGR8;
   BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
-  if (prm->flags & BH8_FLAG_NO_COMPACTION)
-    bh8::bh8_render_kernel<false><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out);
-  else
-    bh8::bh8_render_kernel<true><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out);
+  if (const char* w = std::getenv("BH8_RESOLVE_WAIT")) f.resolve_wait = std::atoi(w);  // tuning knob
+  if (prm->flags & BH8_FLAG_NO_BATCHING) f.resolve_wait = -1;  // exact tests run at once
+  // One instantiation per number of non-central planes with an FP32 side filter; scenes with more
+  // planes than filter slots take the generic instantiation (exact test on every gated step).
+  switch (f.n_nc <= bh8::kMaxFilterPlanes ? f.n_nc : -1) {
+    case 0: bh8::bh8_render_kernel<0><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
+    case 1: bh8::bh8_render_kernel<1><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
+    case 2: bh8::bh8_render_kernel<2><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
+    case 3: bh8::bh8_render_kernel<3><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
+    case 4: bh8::bh8_render_kernel<4><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
+    default: bh8::bh8_render_kernel<-1><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
+  }
   BH8_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   return BH8_OK;

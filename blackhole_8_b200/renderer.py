@@ -26,7 +26,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB
+    path = path or os.environ.get("BH8_LIB_PATH") or LIB
     if not os.path.exists(path):
         raise RuntimeError(
             "%s is missing: build it with `python -m blackhole_8_b200.build` (nvcc, sm_100a). "

@@ -76,7 +76,7 @@ enum {
 
 /* bh8_params.flags */
 #define BH8_FLAG_STATS 1u        /* accumulate bh8_stats counters on the device (tiny cost) */
-#define BH8_FLAG_NO_COMPACTION 2u /* diagnostic: skip the mid-ray block compaction */
+#define BH8_FLAG_NO_BATCHING 2u  /* diagnostic: run every exact segment test at once instead of batching per warp */
 
 typedef struct bh8_camera {
   double pos[3];    /* Camera::focus() */

@@ -22,38 +22,45 @@ struct HostFetch {
   }
 };
 
-extern "C" int bh8_harness_render(const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
-                                  const HarnessTexture* textures, int n_textures, uint8_t* out_bgr,
-                                  uint8_t* out_class, int8_t* out_key, uint16_t* out_steps, char* err) {
-  int rows[BH8_MAX_TEXTURES] = {0}, cols[BH8_MAX_TEXTURES] = {0};
-  for (int i = 0; i < n_textures && i < BH8_MAX_TEXTURES; ++i) {
-    rows[i] = textures[i].rows;
-    cols[i] = textures[i].cols;
-  }
-  Bh8Frame f;
-  const int rc = bh8_build_frame(scene, cam, prm, rows, cols, &f, err);
-  if (rc != BH8_OK) return rc;
-  const HostFetch fetch{textures};
+template <int NN>
+static void trace_frame(const Bh8Frame& f, const HostFetch& fetch, uint8_t* out_bgr, uint8_t* out_class,
+                        int8_t* out_key, uint16_t* out_steps, uint64_t* counters) {
+  const int n_total = 2 * f.nstep - 1;
   for (int y = 0; y < f.height; ++y) {
     for (int x = 0; x < f.width; ++x) {
-      bh8::Ray r;
+      bh8::Ray<NN> r;
+      bh8::Cand c;
       bh8::Hit h;
       h.obj = -1;
+      int steps = 0;
       bool alive = true;
       bh8::ray_setup(f, x, y, r);
       if (r.flags & bh8::kDegenerate) {
-        bh8::ray_degenerate(f, r, h);
+        bh8::ray_degenerate(f, h);
+        steps = 1;
         alive = false;
       }
-      const int nsafe = f.nstep - 1;
-      for (int i = 0; i < f.nstep && alive; ++i)
-        if (bh8::ray_step(f, r, i < nsafe ? r.du : r.du * 0.9, h)) alive = false;
-      if (alive && (r.flags & bh8::kCaptured)) {
-        bh8::ray_chord(f, r, h);
-        alive = false;
+      while (alive) {  // same state machine as the kernel's warp loop, one lane, no batching
+        counters[0]++;
+        if (bh8::ray_advance(f, r, c)) {
+          counters[1]++;
+          if (bh8::ray_resolve(f, r, c, h)) {
+            steps = r.i + 1;
+            break;
+          }
+        } else {
+          bh8::ray_commit(f, r, c);
+        }
+        if (r.i == f.nstep && (r.flags & bh8::kCaptured)) {
+          bh8::ray_chord(f, r, h);
+          steps = r.i;
+          break;
+        }
+        if (r.i >= n_total) {
+          steps = r.i;
+          break;
+        }
       }
-      for (int i = 0; i < nsafe && alive; ++i)
-        if (bh8::ray_step(f, r, -r.du, h)) alive = false;
       uint32_t bgr = 0, oob = 0;
       int cls = BH8_CLASS_BACKGROUND, key = -1;
       if (h.obj >= 0) {
@@ -67,8 +74,34 @@ extern "C" int bh8_harness_render(const bh8_scene* scene, const bh8_camera* cam,
       out_bgr[3 * i + 2] = (bgr >> 16) & 255;
       out_class[i] = (uint8_t)cls;
       out_key[i] = (int8_t)key;
-      out_steps[i] = (uint16_t)r.steps;
+      out_steps[i] = (uint16_t)steps;
     }
+  }
+}
+
+// counters[0] = geodesic updates computed, counters[1] = exact segment tests (ray_resolve calls).
+// filter_slots < 0 forces the generic instantiation (exact test on every gated step).
+extern "C" int bh8_harness_render(const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
+                                  const HarnessTexture* textures, int n_textures, int filter_slots,
+                                  uint8_t* out_bgr, uint8_t* out_class, int8_t* out_key, uint16_t* out_steps,
+                                  uint64_t* counters, char* err) {
+  int rows[BH8_MAX_TEXTURES] = {0}, cols[BH8_MAX_TEXTURES] = {0};
+  for (int i = 0; i < n_textures && i < BH8_MAX_TEXTURES; ++i) {
+    rows[i] = textures[i].rows;
+    cols[i] = textures[i].cols;
+  }
+  Bh8Frame f;
+  const int rc = bh8_build_frame(scene, cam, prm, rows, cols, &f, err);
+  if (rc != BH8_OK) return rc;
+  const HostFetch fetch{textures};
+  counters[0] = counters[1] = 0;
+  switch ((filter_slots >= 0 && f.n_nc <= 4) ? f.n_nc : -1) {
+    case 0: trace_frame<0>(f, fetch, out_bgr, out_class, out_key, out_steps, counters); break;
+    case 1: trace_frame<1>(f, fetch, out_bgr, out_class, out_key, out_steps, counters); break;
+    case 2: trace_frame<2>(f, fetch, out_bgr, out_class, out_key, out_steps, counters); break;
+    case 3: trace_frame<3>(f, fetch, out_bgr, out_class, out_key, out_steps, counters); break;
+    case 4: trace_frame<4>(f, fetch, out_bgr, out_class, out_key, out_steps, counters); break;
+    default: trace_frame<-1>(f, fetch, out_bgr, out_class, out_key, out_steps, counters); break;
   }
   return BH8_OK;
 }

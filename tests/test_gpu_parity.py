@@ -78,11 +78,11 @@ def test_pixel_formats_agree(G):
     assert np.array_equal(a["bgr"], c["bgr"])
 
 
-def test_compaction_does_not_change_any_pixel(G):
+def test_batching_does_not_change_any_pixel(G):
     for name in ("cfg1_640x360", "cfg2_640x360"):
         g = O.load_golden(name)
         a = G.gpu_render(g["snap"])
-        b = G.gpu_render(g["snap"], flags=abi.FLAG_NO_COMPACTION)
+        b = G.gpu_render(g["snap"], flags=abi.FLAG_NO_BATCHING)
         for k in ("bgr", "cls", "key", "steps"):
             assert np.array_equal(a[k], b[k]), (name, k)
 

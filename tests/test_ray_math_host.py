@@ -37,7 +37,7 @@ def harness():
     return _LIB
 
 
-def harness_render(snap, nstep=None):
+def harness_render(snap, nstep=None, filter_slots=4):
     L = harness()
     h, w = snap.height, snap.width
     texs = [O.load_texture(n) for n in snap.textures]
@@ -48,10 +48,14 @@ def harness_render(snap, nstep=None):
     out = {"bgr": np.zeros((h, w, 3), np.uint8), "cls": np.zeros((h, w), np.uint8),
            "key": np.zeros((h, w), np.int8), "steps": np.zeros((h, w), np.uint16)}
     err = C.create_string_buffer(256)
+    counters = (C.c_uint64 * 2)()
     rc = L.bh8_harness_render(C.byref(snap.scene), C.byref(snap.camera), C.byref(prm), tarr, len(texs),
+                              C.c_int(filter_slots),
                               out["bgr"].ctypes.data_as(C.c_void_p), out["cls"].ctypes.data_as(C.c_void_p),
-                              out["key"].ctypes.data_as(C.c_void_p), out["steps"].ctypes.data_as(C.c_void_p), err)
+                              out["key"].ctypes.data_as(C.c_void_p), out["steps"].ctypes.data_as(C.c_void_p),
+                              counters, err)
     assert rc == 0, err.value
+    out["updates"], out["exact_tests"] = int(counters[0]), int(counters[1])
     return out
 
 
@@ -60,5 +64,17 @@ def test_kernel_ray_math_matches_reference_frames(name):
     g = O.load_golden(name)
     got = harness_render(g["snap"])
     rep = parity.assert_parity(got, g, name)
-    print(name, rep)
+    print(name, rep, "exact tests per ray: %.3f" % (got["exact_tests"] / got["cls"].size))
     assert rep["steps_agreement"] > 0.999
+
+
+@pytest.mark.parametrize("name", ["cfg1_640x360", "cfg2_640x360", "cfg5_480x270"])
+def test_generic_instantiation_matches_too(name):
+    """Scenes with more non-central planes than FP32 filter slots take the generic code path
+    (exact test on every gated step); force it here and require the same picture."""
+    g = O.load_golden(name)
+    a = harness_render(g["snap"])
+    b = harness_render(g["snap"], filter_slots=-1)
+    parity.assert_parity(b, g, name)
+    assert np.array_equal(a["cls"], b["cls"]) and np.array_equal(a["steps"], b["steps"])
+    assert b["exact_tests"] > a["exact_tests"]

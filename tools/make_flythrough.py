@@ -3,7 +3,7 @@
 
 oracle/_ref/ref_render --cfg 3 --frame k replays the reference's own Camera::MoveX/RotateZ/MoveY and
 Annulus::RotateZ calls (object.h:58-88) k times and dumps the resulting state; this tool stores, per
-frame, the camera and the vertices of every object in tests/golden/cfg3_flythrough.json (doubles as
+frame, the camera and the vertices of every object in tests/golden/states/cfg3_flythrough.json (doubles as
 %.17g).  Runs only in the build container.
 """
 import json
@@ -30,7 +30,7 @@ def main():
         frames.append({"camera": {k2: d["camera"][k2] for k2 in ("pos", "vx", "vy", "vz")},
                        "v": [o["v"] for o in d["objects"]]})
     base.pop("run", None)
-    with open(os.path.join(ROOT, "tests", "golden", "cfg3_flythrough.json"), "w") as f:
+    with open(os.path.join(ROOT, "tests", "golden", "states", "cfg3_flythrough.json"), "w") as f:
         json.dump({"base": base, "frames": frames}, f)
     print("wrote %d frames" % len(frames))
 
