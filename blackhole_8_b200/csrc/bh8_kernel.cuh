@@ -30,7 +30,7 @@ constexpr int kTileH = 8;
 constexpr int kThreads = kTileW * kTileH;
 constexpr int kMaxFilterPlanes = 4;
 #ifndef BH8_MIN_BLOCKS
-#define BH8_MIN_BLOCKS 3  // CTAs per SM the register allocation is sized for
+#define BH8_MIN_BLOCKS 2  // CTAs per SM the register allocation is sized for
 #endif
 
 struct Bh8Tex {
@@ -83,71 +83,53 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
   const bool inside = x < f.width && y < f.height;
 
   // ---- trace ----------------------------------------------------------------------------------
-  Ray<NN> r;
-  Cand c;
-  Hit h;
-  h.obj = -1;
-  bool alive = inside, pend = false, chord = false;
-  int steps = 0;
-  r.i = 0;
-  if (inside) {
-    ray_setup(f, x, y, r);
-    if (r.flags & kDegenerate) {
-      ray_degenerate(f, h);
-      steps = 1;
-      alive = false;
-    }
-  }
-  const int n_total = 2 * f.nstep - 1;
-  int waited = 0;
-  while (__any_sync(0xffffffffu, alive)) {
-    bool stepped = false;
-    if (alive && !pend) {
-      if (ray_advance(f, r, c)) {
-        pend = true;
-      } else {
-        ray_commit(f, r, c);
-        stepped = true;
-      }
-    }
-    const unsigned pending = __ballot_sync(0xffffffffu, pend);
-    if (pending) {
-      const unsigned running = __ballot_sync(0xffffffffu, alive && !pend);
-      if (running == 0u || ++waited > f.resolve_wait) {
-        waited = 0;
-        if (pend) {
-          pend = false;
-          if (chord) {  // captured ray: straight chord to the centre, :264-272
-            ray_chord(f, r, h);
-            steps = r.i;
-            alive = false;
-          } else if (ray_resolve(f, r, c, h)) {
-            steps = r.i + 1;
-            alive = false;
-          } else {
-            stepped = true;
-          }
+  Lane<NN> L;
+  L.state = kDead;
+  L.hit_obj = -1;
+  L.steps = 0;
+  if (inside) lane_setup(f, x, y, L);
+  // `run`: the lane steps.  `att`: bit 0 = its last update needs the exact test, bit 1 = it reached
+  // an event index.  A lane with att != 0 stops stepping until the warp attends to it.
+  bool run = (L.state == kRun);
+  int att = 0, waited = 0;
+  while (__ballot_sync(0xffffffffu, run) != 0u) {  // some ray of the patch is still travelling
+    // ---- lean stepping: two updates per warp vote ---------------------------------------------
+    for (;;) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (run) {
+          const bool need = lane_update(f, L);
+          att = (need ? 1 : 0) | ((L.i == L.next_evt) ? 2 : 0);
+          run = (att == 0);
         }
       }
+      const unsigned attn = __ballot_sync(0xffffffffu, att != 0);
+      if (attn == 0u) continue;  // nobody needs anything, so some lane is still stepping
+      const unsigned evts = __ballot_sync(0xffffffffu, (att & 2) != 0);
+      const unsigned runs = __ballot_sync(0xffffffffu, run);
+      // Exact tests wait for company: until no lane is stepping any more, an event has to be
+      // handled anyway, or the oldest has waited resolve_wait rounds.
+      if (evts != 0u || runs == 0u || ++waited > f.resolve_wait) break;
     }
-    if (stepped) {
-      if (r.i == f.nstep && (r.flags & kCaptured)) {
-        pend = true;
-        chord = true;
-      } else if (r.i >= n_total) {  // ray ends near r0 without a hit: pixel stays 0
-        steps = r.i;
-        alive = false;
-      }
+    waited = 0;
+    // ---- attend -----------------------------------------------------------------------------------
+    if (att & 1) lane_exact(f, L);
+    if (att != 0 && L.state == kRun && L.i == L.next_evt) {
+      lane_event(f, L);
+      if (L.state == kPendChord) lane_chord(f, L);
     }
+    att = 0;
+    run = (L.state == kRun);
   }
+  const int steps = L.steps;
 
   // ---- colour ------------------------------------------------------------------------------------
   uint32_t bgr = 0, oob = 0;
   int cls = BH8_CLASS_BACKGROUND, key = -1;
-  if (inside && h.obj >= 0) {
-    bgr = shade(f, h.obj, h.p, DeviceFetch{tex}, &oob);
-    cls = f.obj[h.obj].cls;
-    key = f.obj[h.obj].key;
+  if (inside && L.hit_obj >= 0) {
+    bgr = shade(f, L.hit_obj, L.hp, DeviceFetch{tex}, &oob);
+    cls = f.obj[L.hit_obj].cls;
+    key = f.obj[L.hit_obj].key;
   }
   const size_t gi = (size_t)y * f.width + x;
   if (f.pixel_format == BH8_PIXEL_BGR8) {

@@ -25,48 +25,28 @@ struct HostFetch {
 template <int NN>
 static void trace_frame(const Bh8Frame& f, const HostFetch& fetch, uint8_t* out_bgr, uint8_t* out_class,
                         int8_t* out_key, uint16_t* out_steps, uint64_t* counters) {
-  const int n_total = 2 * f.nstep - 1;
   for (int y = 0; y < f.height; ++y) {
     for (int x = 0; x < f.width; ++x) {
-      bh8::Ray<NN> r;
-      bh8::Cand c;
-      bh8::Hit h;
-      h.obj = -1;
-      int steps = 0;
-      bool alive = true;
-      bh8::ray_setup(f, x, y, r);
-      if (r.flags & bh8::kDegenerate) {
-        bh8::ray_degenerate(f, h);
-        steps = 1;
-        alive = false;
-      }
-      while (alive) {  // same state machine as the kernel's warp loop, one lane, no batching
+      bh8::Lane<NN> L;
+      bh8::lane_setup(f, x, y, L);
+      while (L.state == bh8::kRun) {  // the kernel's per-lane sequence, one lane, no batching
         counters[0]++;
-        if (bh8::ray_advance(f, r, c)) {
+        const bool need = bh8::lane_update(f, L);
+        if (need) {
           counters[1]++;
-          if (bh8::ray_resolve(f, r, c, h)) {
-            steps = r.i + 1;
-            break;
-          }
-        } else {
-          bh8::ray_commit(f, r, c);
+          bh8::lane_exact(f, L);
         }
-        if (r.i == f.nstep && (r.flags & bh8::kCaptured)) {
-          bh8::ray_chord(f, r, h);
-          steps = r.i;
-          break;
-        }
-        if (r.i >= n_total) {
-          steps = r.i;
-          break;
+        if (L.state == bh8::kRun && L.i == L.next_evt) {
+          bh8::lane_event(f, L);
+          if (L.state == bh8::kPendChord) bh8::lane_chord(f, L);
         }
       }
       uint32_t bgr = 0, oob = 0;
       int cls = BH8_CLASS_BACKGROUND, key = -1;
-      if (h.obj >= 0) {
-        bgr = bh8::shade(f, h.obj, h.p, fetch, &oob);
-        cls = f.obj[h.obj].cls;
-        key = f.obj[h.obj].key;
+      if (L.hit_obj >= 0) {
+        bgr = bh8::shade(f, L.hit_obj, L.hp, fetch, &oob);
+        cls = f.obj[L.hit_obj].cls;
+        key = f.obj[L.hit_obj].key;
       }
       const size_t i = static_cast<size_t>(y) * f.width + x;
       out_bgr[3 * i] = bgr & 255;
@@ -74,7 +54,7 @@ static void trace_frame(const Bh8Frame& f, const HostFetch& fetch, uint8_t* out_
       out_bgr[3 * i + 2] = (bgr >> 16) & 255;
       out_class[i] = (uint8_t)cls;
       out_key[i] = (int8_t)key;
-      out_steps[i] = (uint16_t)steps;
+      out_steps[i] = (uint16_t)L.steps;
     }
   }
 }
