@@ -1,0 +1,73 @@
+// blackhole_solution_gpu -- GPU counterpart of the reference's blackhole_solution_test driver.
+//
+// Same scene construction through the same header API (include/blackhole), same frame loop shape
+// (render, "Took N ms", hand the frame to the video writer, move the camera / spin the disc,
+// blackhole_solution_test.cc:153-408) -- but the per-pixel loop of :161-308 is one call into the
+// CUDA renderer.  Headless: runs a scripted number of frames instead of reading keys.
+//
+//   blackhole_solution_gpu [--cfg N] [--width W] [--height H] [--frames K] [--nstep S]
+//                          [--texdir DIR] [--out PREFIX]
+// Writes PREFIX_<frame>.bgr (raw: int32 rows, int32 cols, BGR bytes) when --out is given.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+
+#include "blackhole/gpu/renderer.h"
+#include "scenes.h"  // oracle/scenes.h: the BASELINE scenes, written against the public header API
+
+int main(int argc, char** argv) {
+  int cfg = 0, width = 960, height = 540, frames = 1, nstep = -1;
+  std::string texdir = "build/textures", out;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
+    if (a == "--cfg") cfg = std::atoi(next());
+    else if (a == "--width") width = std::atoi(next());
+    else if (a == "--height") height = std::atoi(next());
+    else if (a == "--frames") frames = std::atoi(next());
+    else if (a == "--nstep") nstep = std::atoi(next());
+    else if (a == "--texdir") texdir = next();
+    else if (a == "--out") out = next();
+    else {
+      std::fprintf(stderr, "unknown argument %s\n", a.c_str());
+      return 2;
+    }
+  }
+  bh8scenes::Scene* scene = bh8scenes::Build(cfg, width, height, 0, texdir);
+  if (!scene) {
+    std::fprintf(stderr, "unknown cfg %d\n", cfg);
+    return 2;
+  }
+  if (nstep <= 0) nstep = scene->nstep;
+  auto& manager = bh8scenes::manager_type::GetInstance();
+
+  try {
+    blackhole::gpu::Renderer gpu;
+    cv::Mat screen;
+    for (int k = 0; k < frames; ++k) {
+      const auto t1 = std::chrono::high_resolution_clock::now();
+      gpu.Render(manager, *scene->blackhole, scene->camera, &screen, nstep);
+      const auto t2 = std::chrono::high_resolution_clock::now();
+      const auto us = std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
+      std::cout << "Took " << us / 1000.0 << "ms (kernel " << gpu.last_stats().kernel_ms << "ms, "
+                << gpu.last_stats().steps << " geodesic steps)\n";
+      if (!out.empty()) cv::imwrite(out + "_" + std::to_string(k), screen);
+      // frame loop tail, blackhole_solution_test.cc:346-407: fly-through script + disc spin
+      if (cfg == 3) {
+        if (k < 120) {
+          scene->camera.MoveX(10);
+        } else {
+          scene->camera.RotateZ(blackhole::pi / 1800.0 * 10);
+          scene->camera.MoveY(10);
+        }
+      }
+      if (scene->disc) scene->disc->RotateZ(blackhole::pi / 180);
+    }
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

@@ -54,6 +54,75 @@ struct DeviceFetch {
   }
 };
 
+// Register budget.  The stepping loop needs ~50 registers, the exact segment test + shading ~110.
+// Letting the second set the kernel's register count would halve the occupancy that hides the FP64
+// pipe's latency, so a lane that enters the exact test first parks its whole state in a per-thread
+// mailbox in shared memory and re-loads it afterwards: no stepping value is live inside the test,
+// and the test is entered about once per ray.  (volatile: the compiler must not forward the stores
+// to the loads, which would keep the values alive in registers.)
+// Mailbox, stride kThreads: doubles [0..2] e2 (written at setup), [3..10] the Lane's doubles;
+// ints [0..11] the Lane's integers, [12..] fa/fb bit patterns.
+constexpr int kMailDoubles = 11;
+constexpr int kMailInts = 12 + 2 * kMaxFilterPlanes;
+
+template <int NN>
+__device__ __forceinline__ void lane_park(const Lane<NN>& L, volatile double* md, volatile int* mi) {
+  md[3 * kThreads] = L.u;
+  md[4 * kThreads] = L.phi;
+  md[5 * kThreads] = L.dphi_prev;
+  md[6 * kThreads] = L.du_h;
+  md[7 * kThreads] = L.delta;
+  md[8 * kThreads] = L.binv2;
+  md[9 * kThreads] = L.phi_trig;
+  md[10 * kThreads] = L.t;
+  mi[0 * kThreads] = L.i;
+  mi[1 * kThreads] = L.next_evt;
+  mi[2 * kThreads] = L.state;
+  mi[3 * kThreads] = L.flags;
+  mi[4 * kThreads] = (int)L.fbits;
+  mi[5 * kThreads] = L.fstep;
+  mi[6 * kThreads] = L.gate_in;
+  mi[7 * kThreads] = L.gate_out;
+  mi[8 * kThreads] = L.steps;
+  mi[9 * kThreads] = L.hit_obj;
+  mi[10 * kThreads] = (int)L.bgr;
+  mi[11 * kThreads] = (int)L.oob;
+#pragma unroll
+  for (int j = 0; j < (NN > 0 ? NN : 0); ++j) {
+    mi[(12 + 2 * j) * kThreads] = __float_as_int(L.fa[j]);
+    mi[(13 + 2 * j) * kThreads] = __float_as_int(L.fb[j]);
+  }
+}
+
+template <int NN>
+__device__ __forceinline__ void lane_unpark(Lane<NN>& L, const volatile double* md, const volatile int* mi) {
+  L.u = md[3 * kThreads];
+  L.phi = md[4 * kThreads];
+  L.dphi_prev = md[5 * kThreads];
+  L.du_h = md[6 * kThreads];
+  L.delta = md[7 * kThreads];
+  L.binv2 = md[8 * kThreads];
+  L.phi_trig = md[9 * kThreads];
+  L.t = md[10 * kThreads];
+  L.i = mi[0 * kThreads];
+  L.next_evt = mi[1 * kThreads];
+  L.state = mi[2 * kThreads];
+  L.flags = mi[3 * kThreads];
+  L.fbits = (uint32_t)mi[4 * kThreads];
+  L.fstep = mi[5 * kThreads];
+  L.gate_in = mi[6 * kThreads];
+  L.gate_out = mi[7 * kThreads];
+  L.steps = mi[8 * kThreads];
+  L.hit_obj = mi[9 * kThreads];
+  L.bgr = (uint32_t)mi[10 * kThreads];
+  L.oob = (uint32_t)mi[11 * kThreads];
+#pragma unroll
+  for (int j = 0; j < (NN > 0 ? NN : 0); ++j) {
+    L.fa[j] = __int_as_float(mi[(12 + 2 * j) * kThreads]);
+    L.fb[j] = __int_as_float(mi[(13 + 2 * j) * kThreads]);
+  }
+}
+
 template <int NN>
 __global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
 bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
@@ -83,51 +152,52 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
   const bool inside = x < f.width && y < f.height;
 
   // ---- trace ----------------------------------------------------------------------------------
+  __shared__ double sh_md[kMailDoubles * kThreads];
+  __shared__ int sh_mi[kMailInts * kThreads];
+  double* const md = sh_md + tid;
+  int* const mi = sh_mi + tid;
+  const E2Ref e2r{md, kThreads};
   Lane<NN> L;
   L.state = kDead;
   L.hit_obj = -1;
   L.steps = 0;
-  if (inside) lane_setup(f, x, y, L);
-  // `run`: the lane steps.  `att`: bit 0 = its last update needs the exact test, bit 1 = it reached
-  // an event index.  A lane with att != 0 stops stepping until the warp attends to it.
-  bool run = (L.state == kRun);
-  int att = 0, waited = 0;
-  while (__ballot_sync(0xffffffffu, run) != 0u) {  // some ray of the patch is still travelling
-    // ---- lean stepping: two updates per warp vote ---------------------------------------------
-    for (;;) {
+  L.bgr = 0;
+  L.oob = 0;
+  if (inside) lane_setup(f, x, y, L, e2r);
+  int waited = 0;
+  for (;;) {
+    // lean stepping: two updates per pair of warp votes
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (run) {
-          const bool need = lane_update(f, L);
-          att = (need ? 1 : 0) | ((L.i == L.next_evt) ? 2 : 0);
-          run = (att == 0);
-        }
-      }
-      const unsigned attn = __ballot_sync(0xffffffffu, att != 0);
-      if (attn == 0u) continue;  // nobody needs anything, so some lane is still stepping
-      const unsigned evts = __ballot_sync(0xffffffffu, (att & 2) != 0);
-      const unsigned runs = __ballot_sync(0xffffffffu, run);
-      // Exact tests wait for company: until no lane is stepping any more, an event has to be
-      // handled anyway, or the oldest has waited resolve_wait rounds.
-      if (evts != 0u || runs == 0u || ++waited > f.resolve_wait) break;
+    for (int k = 0; k < 2; ++k)
+      if (L.state == kRun) lane_update(f, L);
+    const unsigned runs = __ballot_sync(0xffffffffu, L.state == kRun);
+    const unsigned pend = __ballot_sync(0xffffffffu, (unsigned)(L.state - kPend) < 2u);
+    if (pend == 0u) {
+      if (runs == 0u) break;  // every ray of the patch has ended
+      continue;
     }
+    // Parked exact tests wait for company: until no lane is stepping any more or the oldest has
+    // waited resolve_wait rounds; then all of them run together.
+    if (runs != 0u && ++waited <= f.resolve_wait) continue;
     waited = 0;
-    // ---- attend -----------------------------------------------------------------------------------
-    if (att & 1) lane_exact(f, L);
-    if (att != 0 && L.state == kRun && L.i == L.next_evt) {
-      lane_event(f, L);
-      if (L.state == kPendChord) lane_chord(f, L);
+    if ((unsigned)(L.state - kPend) < 2u) {
+      lane_park(L, md, mi);
+      {
+        Lane<NN> T;  // the test works on its own copy, loaded from the mailbox
+        lane_unpark(T, md, mi);
+        lane_exact(f, T, e2r, DeviceFetch{tex});
+        if (T.state == kPendChord) lane_exact(f, T, e2r, DeviceFetch{tex});  // event after a cleared segment
+        lane_park(T, md, mi);
+      }
+      lane_unpark(L, md, mi);
     }
-    att = 0;
-    run = (L.state == kRun);
   }
   const int steps = L.steps;
 
   // ---- colour ------------------------------------------------------------------------------------
-  uint32_t bgr = 0, oob = 0;
+  const uint32_t bgr = L.bgr, oob = L.oob;
   int cls = BH8_CLASS_BACKGROUND, key = -1;
   if (inside && L.hit_obj >= 0) {
-    bgr = shade(f, L.hit_obj, L.hp, DeviceFetch{tex}, &oob);
     cls = f.obj[L.hit_obj].cls;
     key = f.obj[L.hit_obj].key;
   }

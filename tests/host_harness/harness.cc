@@ -28,23 +28,21 @@ static void trace_frame(const Bh8Frame& f, const HostFetch& fetch, uint8_t* out_
   for (int y = 0; y < f.height; ++y) {
     for (int x = 0; x < f.width; ++x) {
       bh8::Lane<NN> L;
-      bh8::lane_setup(f, x, y, L);
-      while (L.state == bh8::kRun) {  // the kernel's per-lane sequence, one lane, no batching
-        counters[0]++;
-        const bool need = bh8::lane_update(f, L);
-        if (need) {
+      double e2[3];
+      const bh8::E2Ref e2r{e2, 1};
+      bh8::lane_setup(f, x, y, L, e2r);
+      while (L.state != bh8::kDead) {  // the kernel's per-lane sequence, one lane, no batching
+        if (L.state == bh8::kRun) {
+          counters[0]++;
+          bh8::lane_update(f, L);
+        } else {
           counters[1]++;
-          bh8::lane_exact(f, L);
-        }
-        if (L.state == bh8::kRun && L.i == L.next_evt) {
-          bh8::lane_event(f, L);
-          if (L.state == bh8::kPendChord) bh8::lane_chord(f, L);
+          bh8::lane_exact(f, L, e2r, fetch);
         }
       }
-      uint32_t bgr = 0, oob = 0;
+      const uint32_t bgr = L.bgr;
       int cls = BH8_CLASS_BACKGROUND, key = -1;
       if (L.hit_obj >= 0) {
-        bgr = bh8::shade(f, L.hit_obj, L.hp, fetch, &oob);
         cls = f.obj[L.hit_obj].cls;
         key = f.obj[L.hit_obj].key;
       }
