@@ -219,8 +219,10 @@ def main():
 
     # frames this rank renders: N == 1 -> the configs[1] frame every step; N > 1 -> fly-through frames
     if world > 1:
+        from blackhole_8_b200 import sharding
         fly = flythrough_snapshots(240)
-        my_frames = [fly[(i * world + rank) % 240] for i in range(args.steps + args.warmup)]
+        # step i of the job renders frames i*world .. i*world+world-1; rank r owns frame i*world + r
+        my_frames = [fly[k % 240] for k in sharding.frames_of((args.steps + args.warmup) * world, rank, world)]
     else:
         my_frames = [base] * (args.steps + args.warmup)
 
@@ -241,7 +243,8 @@ def main():
     local_flush = r.frame_alloc(flush_bytes)  # each rank flushes its own GPU's L2
 
     def slot_ptr(step):
-        return ring + ((step % ring_slots) * world + rank) * frame_bytes
+        from blackhole_8_b200 import sharding
+        return ring + sharding.ring_slot_offset(step, rank, world, ring_slots, frame_bytes)
 
     # one untimed launch with counters: steps / class mix of this rank's first frame
     r.render_device(my_frames[0], slot_ptr(0), flags=flags | abi.FLAG_STATS)

@@ -54,44 +54,48 @@ struct DeviceFetch {
   }
 };
 
-// Register budget.  The stepping loop needs ~50 registers, the exact segment test + shading ~110.
-// Letting the second set the kernel's register count would halve the occupancy that hides the FP64
-// pipe's latency, so a lane that enters the exact test first parks its whole state in a per-thread
-// mailbox in shared memory and re-loads it afterwards: no stepping value is live inside the test,
-// and the test is entered about once per ray.  (volatile: the compiler must not forward the stores
-// to the loads, which would keep the values alive in registers.)
-// Mailbox, stride kThreads: doubles [0..2] e2 (written at setup), [3..10] the Lane's doubles;
-// ints [0..11] the Lane's integers, [12..] fa/fb bit patterns.
+// Register budget.  The stepping loop needs ~50 registers, the exact segment test ~110.  Letting the
+// second set the kernel's register count would halve the occupancy that hides the FP64 pipe's
+// latency, so a lane that enters the exact test first parks its state in a per-thread mailbox in
+// shared memory and re-loads it afterwards: no stepping value is live inside the test, and the test
+// is entered about once per ray.  (volatile: the compiler must not forward the stores to the loads,
+// which would keep the values alive in registers.)
+// Mailbox, stride kThreads.  doubles: [0..2] e2 (hit point once the ray has ended), [3] u, [4] phi,
+// [5] dphi_prev, [6] delta, [7] phi_trig, [8] t, [9] du_h, [10] binv2.  ints: [0] i, [1] next_evt,
+// [2] state, [3] fbits, [4] fstep, [5] steps, [6] hit_obj, [7] flags, [8] gate_in, [9] gate_out,
+// [10..] fa/fb bit patterns.  Slots from du_h / flags on never change after setup: written once.
 constexpr int kMailDoubles = 11;
-constexpr int kMailInts = 12 + 2 * kMaxFilterPlanes;
+constexpr int kMailInts = 10 + 2 * kMaxFilterPlanes;
+
+template <int NN>
+__device__ __forceinline__ void lane_park_constants(const Lane<NN>& L, volatile double* md, volatile int* mi) {
+  md[9 * kThreads] = L.du_h;
+  md[10 * kThreads] = L.binv2;
+  mi[7 * kThreads] = L.flags;
+  mi[8 * kThreads] = L.gate_in;
+  mi[9 * kThreads] = L.gate_out;
+#pragma unroll
+  for (int j = 0; j < (NN > 0 ? NN : 0); ++j) {
+    mi[(10 + 2 * j) * kThreads] = __float_as_int(L.fa[j]);
+    mi[(11 + 2 * j) * kThreads] = __float_as_int(L.fb[j]);
+  }
+}
 
 template <int NN>
 __device__ __forceinline__ void lane_park(const Lane<NN>& L, volatile double* md, volatile int* mi) {
   md[3 * kThreads] = L.u;
   md[4 * kThreads] = L.phi;
   md[5 * kThreads] = L.dphi_prev;
-  md[6 * kThreads] = L.du_h;
-  md[7 * kThreads] = L.delta;
-  md[8 * kThreads] = L.binv2;
-  md[9 * kThreads] = L.phi_trig;
-  md[10 * kThreads] = L.t;
+  md[6 * kThreads] = L.delta;
+  md[7 * kThreads] = L.phi_trig;
+  md[8 * kThreads] = L.t;
   mi[0 * kThreads] = L.i;
   mi[1 * kThreads] = L.next_evt;
   mi[2 * kThreads] = L.state;
-  mi[3 * kThreads] = L.flags;
-  mi[4 * kThreads] = (int)L.fbits;
-  mi[5 * kThreads] = L.fstep;
-  mi[6 * kThreads] = L.gate_in;
-  mi[7 * kThreads] = L.gate_out;
-  mi[8 * kThreads] = L.steps;
-  mi[9 * kThreads] = L.hit_obj;
-  mi[10 * kThreads] = (int)L.bgr;
-  mi[11 * kThreads] = (int)L.oob;
-#pragma unroll
-  for (int j = 0; j < (NN > 0 ? NN : 0); ++j) {
-    mi[(12 + 2 * j) * kThreads] = __float_as_int(L.fa[j]);
-    mi[(13 + 2 * j) * kThreads] = __float_as_int(L.fb[j]);
-  }
+  mi[3 * kThreads] = (int)L.fbits;
+  mi[4 * kThreads] = L.fstep;
+  mi[5 * kThreads] = L.steps;
+  mi[6 * kThreads] = L.hit_obj;
 }
 
 template <int NN>
@@ -99,28 +103,28 @@ __device__ __forceinline__ void lane_unpark(Lane<NN>& L, const volatile double* 
   L.u = md[3 * kThreads];
   L.phi = md[4 * kThreads];
   L.dphi_prev = md[5 * kThreads];
-  L.du_h = md[6 * kThreads];
-  L.delta = md[7 * kThreads];
-  L.binv2 = md[8 * kThreads];
-  L.phi_trig = md[9 * kThreads];
-  L.t = md[10 * kThreads];
+  L.delta = md[6 * kThreads];
+  L.phi_trig = md[7 * kThreads];
+  L.t = md[8 * kThreads];
+  L.du_h = md[9 * kThreads];
+  L.binv2 = md[10 * kThreads];
   L.i = mi[0 * kThreads];
   L.next_evt = mi[1 * kThreads];
   L.state = mi[2 * kThreads];
-  L.flags = mi[3 * kThreads];
-  L.fbits = (uint32_t)mi[4 * kThreads];
-  L.fstep = mi[5 * kThreads];
-  L.gate_in = mi[6 * kThreads];
-  L.gate_out = mi[7 * kThreads];
-  L.steps = mi[8 * kThreads];
-  L.hit_obj = mi[9 * kThreads];
-  L.bgr = (uint32_t)mi[10 * kThreads];
-  L.oob = (uint32_t)mi[11 * kThreads];
+  L.fbits = (uint32_t)mi[3 * kThreads];
+  L.fstep = mi[4 * kThreads];
+  L.steps = mi[5 * kThreads];
+  L.hit_obj = mi[6 * kThreads];
+  L.flags = mi[7 * kThreads];
+  L.gate_in = mi[8 * kThreads];
+  L.gate_out = mi[9 * kThreads];
 #pragma unroll
   for (int j = 0; j < (NN > 0 ? NN : 0); ++j) {
-    L.fa[j] = __int_as_float(mi[(12 + 2 * j) * kThreads]);
-    L.fb[j] = __int_as_float(mi[(13 + 2 * j) * kThreads]);
+    L.fa[j] = __int_as_float(mi[(10 + 2 * j) * kThreads]);
+    L.fb[j] = __int_as_float(mi[(11 + 2 * j) * kThreads]);
   }
+  L.bgr = 0;
+  L.oob = 0;
 }
 
 template <int NN>
@@ -163,7 +167,10 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
   L.steps = 0;
   L.bgr = 0;
   L.oob = 0;
-  if (inside) lane_setup(f, x, y, L, e2r);
+  if (inside) {
+    lane_setup(f, x, y, L, e2r);
+    lane_park_constants(L, md, mi);
+  }
   int waited = 0;
   for (;;) {
     // lean stepping: two updates per pair of warp votes
@@ -185,8 +192,8 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
       {
         Lane<NN> T;  // the test works on its own copy, loaded from the mailbox
         lane_unpark(T, md, mi);
-        lane_exact(f, T, e2r, DeviceFetch{tex});
-        if (T.state == kPendChord) lane_exact(f, T, e2r, DeviceFetch{tex});  // event after a cleared segment
+        lane_exact(f, T, e2r);
+        if (T.state == kPendChord) lane_exact(f, T, e2r);  // event right after a cleared segment
         lane_park(T, md, mi);
       }
       lane_unpark(L, md, mi);
@@ -195,6 +202,9 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
   const int steps = L.steps;
 
   // ---- colour ------------------------------------------------------------------------------------
+  if (!inside) L.hit_obj = -1;
+  L.oob = 0;
+  lane_shade(f, L, e2r, DeviceFetch{tex});
   const uint32_t bgr = L.bgr, oob = L.oob;
   int cls = BH8_CLASS_BACKGROUND, key = -1;
   if (inside && L.hit_obj >= 0) {

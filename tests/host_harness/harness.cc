@@ -37,9 +37,10 @@ static void trace_frame(const Bh8Frame& f, const HostFetch& fetch, uint8_t* out_
           bh8::lane_update(f, L);
         } else {
           counters[1]++;
-          bh8::lane_exact(f, L, e2r, fetch);
+          bh8::lane_exact(f, L, e2r);
         }
       }
+      bh8::lane_shade(f, L, e2r, fetch);
       const uint32_t bgr = L.bgr;
       int cls = BH8_CLASS_BACKGROUND, key = -1;
       if (L.hit_obj >= 0) {
