@@ -37,6 +37,7 @@ struct Device {
   cudaEvent_t ev_copy_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   bool timing_open = false;
+  bool slot_busy[2] = {false, false};  // bh8_submit: a frame whose read-back has not been waited for
 };
 
 }  // namespace
@@ -48,6 +49,7 @@ struct bh8_ctx {
   int tex_cols[BH8_MAX_TEXTURES] = {};
   std::string err;
   uint64_t launches = 0;
+  uint64_t next_ticket = 0;  // bh8_submit
   std::vector<void*> owned;  // bh8_frame_alloc results (device 0)
 };
 
@@ -482,6 +484,52 @@ int bh8_render(bh8_ctx* ctx, const bh8_scene* scenes, const bh8_camera* cams, in
     stats->kernel_ms = kernel_ms;
     stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   }
+  return BH8_OK;
+}
+
+int bh8_submit(bh8_ctx* ctx, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* params,
+               uint8_t* out_pixels, uint64_t* ticket) {
+  if (!ctx) return BH8_EINVAL;
+  if (!scene || !cam || !params || !out_pixels || !ticket) return fail(ctx, BH8_EINVAL, "bad arguments to bh8_submit");
+  const uint64_t t = ctx->next_ticket;
+  Device& d = ctx->dev[t % ctx->n_dev];
+  const int b = static_cast<int>((t / ctx->n_dev) & 1);
+  const size_t npx = static_cast<size_t>(cam->width) * cam->height;
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  if (d.cap_pixels < npx) {
+    const int rc = ensure_staging(ctx, d, npx);
+    if (rc != BH8_OK) return rc;
+    d.slot_busy[0] = d.slot_busy[1] = false;
+  }
+  if (d.slot_busy[b]) {  // the frame submitted two rounds ago on this device still owns the buffer
+    BH8_CUDA(ctx, cudaEventSynchronize(d.ev_copy_done[b]));
+    d.slot_busy[b] = false;
+  }
+  bh8_params p = *params;
+  p.shard_count = 0;
+  p.shard_index = 0;
+  const int rc = launch_frame(ctx, d, scene, cam, &p, d.d_pix[b], nullptr, nullptr, nullptr);
+  if (rc != BH8_OK) return rc;
+  BH8_CUDA(ctx, cudaEventRecord(d.ev_kernel_done[b], d.stream));
+  BH8_CUDA(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_kernel_done[b], 0));
+  BH8_CUDA(ctx, cudaMemcpyAsync(out_pixels, d.d_pix[b], npx * bh8_pixel_bytes(p.pixel_format), cudaMemcpyDeviceToHost,
+                                d.copy_stream));
+  BH8_CUDA(ctx, cudaEventRecord(d.ev_copy_done[b], d.copy_stream));
+  d.slot_busy[b] = true;
+  *ticket = t;
+  ctx->next_ticket = t + 1;
+  return BH8_OK;
+}
+
+int bh8_wait(bh8_ctx* ctx, uint64_t ticket) {
+  if (!ctx) return BH8_EINVAL;
+  if (ticket >= ctx->next_ticket) return fail(ctx, BH8_EINVAL, "bh8_wait: unknown ticket");
+  if (ticket + 2ull * ctx->n_dev < ctx->next_ticket) return BH8_OK;  // its buffer was already recycled => done
+  Device& d = ctx->dev[ticket % ctx->n_dev];
+  const int b = static_cast<int>((ticket / ctx->n_dev) & 1);
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  BH8_CUDA(ctx, cudaEventSynchronize(d.ev_copy_done[b]));
+  d.slot_busy[b] = false;
   return BH8_OK;
 }
 

@@ -43,6 +43,9 @@ def load_library(path=None):
         "bh8_set_texture": (i32, [vp, i32, vp, i32, i32, C.c_size_t]),
         "bh8_render": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), i32, C.POINTER(abi.Params),
                              vp, vp, vp, vp, C.POINTER(abi.Stats)]),
+        "bh8_submit": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params), vp,
+                             C.POINTER(u64)]),
+        "bh8_wait": (i32, [vp, u64]),
         "bh8_render_device": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params),
                                     vp, vp, vp, vp]),
         "bh8_sync": (i32, [vp]),
@@ -171,6 +174,19 @@ class Renderer:
         if stats:
             res["stats"] = st
         return res
+
+    # -- streaming host-buffer path ------------------------------------------------------------------
+    def submit(self, snap, out_array, nstep=None, pixel_format=abi.PIXEL_RGBA8, flags=0):
+        """Launch one frame and queue its read-back into out_array (pinned host memory); returns a
+        ticket for wait().  Two frames per device may be in flight."""
+        prm = abi.Params(nstep or snap.nstep, pixel_format, flags, 0, 0, 0)
+        t = C.c_uint64()
+        self._check(self.lib.bh8_submit(self._ctx, C.byref(snap.scene), C.byref(snap.camera), C.byref(prm),
+                                        out_array.ctypes.data_as(C.c_void_p), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        self._check(self.lib.bh8_wait(self._ctx, C.c_uint64(ticket)))
 
     # -- device-resident path --------------------------------------------------------------------------
     def frame_alloc(self, nbytes):

@@ -154,6 +154,15 @@ int bh8_render(bh8_ctx* ctx, const bh8_scene* scenes, const bh8_camera* cams, in
                const bh8_params* params, uint8_t* out_pixels, uint8_t* out_class, int8_t* out_key,
                uint16_t* out_steps, bh8_stats* stats);
 
+/* Streaming form of bh8_render for one frame at a time: bh8_submit() launches the frame and queues
+ * its read-back into out_pixels (HOST memory, ideally from bh8_host_alloc) and returns at once with
+ * a ticket; bh8_wait() blocks until that frame is complete in out_pixels.  Two frames per device
+ * may be in flight, so the copy of frame k overlaps the kernel of frame k+1; frames go to the
+ * context's devices round-robin.  Tickets must be waited for in order of submission. */
+int bh8_submit(bh8_ctx* ctx, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* params,
+               uint8_t* out_pixels, uint64_t* ticket);
+int bh8_wait(bh8_ctx* ctx, uint64_t ticket);
+
 /* Device-resident path (device 0 of the context).  d_pixels / d_class / d_key / d_steps are DEVICE
  * pointers for ONE frame -- they may be peer / IPC mappings of another GPU's memory, in which case
  * the kernel's stores go over NVLink and no separate gather copy is needed.  Asynchronous on the

@@ -147,3 +147,22 @@ def test_errors_are_loud(G):
     d["bh_index"] = 1
     with pytest.raises(Bh8Error):
         r.render(abi.SceneSnapshot.from_dict(d))
+
+
+def test_streaming_submit_wait_equals_render(G):
+    r = G.renderer()
+    snaps = [O.load_golden(n)["snap"] for n in ("cfg3_frame60_480x270", "cfg3_frame180_480x270")]
+    r.set_textures(snaps[0], O.load_texture)
+    bufs = [r.pinned((270, 480, 4)) for _ in range(2)]
+    want = [r.render(s, pixel_format=abi.PIXEL_RGBA8)["pixels"][0].copy() for s in snaps]
+    prev = None
+    for k in range(7):  # more submissions than buffers: slots are recycled
+        t = r.submit(snaps[k & 1], bufs[k & 1].array)
+        if prev is not None:
+            r.wait(prev[0])
+            assert np.array_equal(bufs[prev[1]].array, want[prev[1]])
+        prev = (t, k & 1)
+    r.wait(prev[0])
+    assert np.array_equal(bufs[prev[1]].array, want[prev[1]])
+    for b in bufs:
+        b.free()
