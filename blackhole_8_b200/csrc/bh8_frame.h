@@ -44,8 +44,13 @@ struct Bh8Frame {
   double FF;              // F . F
   double mass, two_m, b_c2 /* b_c^2 */, inv3m, R, R2;
   double r0, u0;          // |F| and 1/|F|: convertedCameraFocus has the length of F
-  double bis_mid0;                    // first bisection midpoint
-  double bis_h[BH8_BISECT_ITERS + 1]; // bis_h[i] = (r - l) / 2^(i+1): +- offset applied after test i-1; [20] = final width
+  // SolveG's bisection (blackhole_solution.h:35-53) on [l0, r0] = [cbrt(eps), 1/(3M)]: after test i
+  // (0-based) the midpoint moves by bis_h[i] = (r0 - l0) / 2^(i+2); the result lies on the grid
+  // l0 + K * bis_grid, bis_grid = (r0 - l0) / 2^20.
+  double bis_mid0;
+  double bis_h[BH8_BISECT_ITERS + 1];
+  double bis_l0, bis_grid, bis_inv_grid;
+  double nine_m2;         // (3M)^2: q = nine_m2 / b^2 is the constant term of the normalised cubic
   // integration
   int32_t nstep, n_obj, bh_index, n_central;
   double inv_nstep;
@@ -135,6 +140,10 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
     const double l = 0.0 + cbrt(2.220446049250313e-16);
     const double r = f->inv3m;
     f->bis_mid0 = (l + r) / 2.0;
+    f->bis_l0 = l;
+    f->bis_grid = (r - l) / 1048576.0;
+    f->bis_inv_grid = 1048576.0 / (r - l);
+    f->nine_m2 = 9.0 * bho->mass * bho->mass;
     double h = (r - l) / 2.0;
     for (int i = 0; i <= BH8_BISECT_ITERS; ++i) {
       h /= 2.0;

@@ -29,6 +29,9 @@ constexpr int kTileW = 32;
 constexpr int kTileH = 8;
 constexpr int kThreads = kTileW * kTileH;
 constexpr int kMaxFilterPlanes = 4;
+#ifndef BH8_UPDATES_PER_VOTE
+#define BH8_UPDATES_PER_VOTE 2  // geodesic updates between two rounds of warp votes
+#endif
 #ifndef BH8_MIN_BLOCKS
 #define BH8_MIN_BLOCKS 5  // CTAs per SM the register allocation is sized for (measured best of 2..5 on B200)
 #endif
@@ -173,9 +176,9 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
   }
   int waited = 0;
   for (;;) {
-    // lean stepping: two updates per pair of warp votes
+    // lean stepping: a few updates per pair of warp votes
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k)
       if (L.state == kRun) lane_update(f, L);
     const unsigned runs = __ballot_sync(0xffffffffu, L.state == kRun);
     const unsigned pend = __ballot_sync(0xffffffffu, (unsigned)(L.state - kPend) < 2u);

@@ -5,6 +5,7 @@
 // tests/host_harness/_build/; the product library never contains or calls it -- there is no CPU
 // rendering path in libbh8.so.
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 
 #include "bh8_ray.cuh"
@@ -83,4 +84,33 @@ extern "C" int bh8_harness_render(const bh8_scene* scene, const bh8_camera* cam,
     default: trace_frame<-1>(f, fetch, out_bgr, out_class, out_key, out_steps, counters); break;
   }
   return BH8_OK;
+}
+
+// Known-answer hook: turning point by the fast path vs the literal bisection, same frame constants.
+extern "C" int bh8_harness_solve(double mass, const double* b, int n, double* fast, double* bisect) {
+  Bh8Frame f;
+  std::memset(&f, 0, sizeof f);
+  f.two_m = 2.0 * mass;
+  f.inv3m = 1.0 / (3.0 * mass);
+  f.nine_m2 = 9.0 * mass * mass;
+  const double l = 0.0 + cbrt(2.220446049250313e-16), r = f.inv3m;
+  f.bis_mid0 = (l + r) / 2.0;
+  double h = (r - l) / 2.0;
+  for (int i = 0; i <= BH8_BISECT_ITERS; ++i) {
+    h /= 2.0;
+    f.bis_h[i] = h;
+  }
+  f.bis_l0 = l;
+  f.bis_grid = (r - l) / 1048576.0;
+  f.bis_inv_grid = 1048576.0 / (r - l);
+  for (int i = 0; i < n; ++i) {
+    const double binv2 = 1.0 / (b[i] * b[i]);
+    fast[i] = bh8::solve_turning_point(f, binv2);
+    bisect[i] = bh8::solve_turning_point_bisect(f, binv2);
+  }
+  return 0;
+}
+
+extern "C" void bh8_harness_sincos(const double* x, int n, double* s, double* c) {
+  for (int i = 0; i < n; ++i) bh8::sincos_(x[i], &s[i], &c[i]);
 }

@@ -78,3 +78,41 @@ def test_generic_instantiation_matches_too(name):
     parity.assert_parity(b, g, name)
     assert np.array_equal(a["cls"], b["cls"]) and np.array_equal(a["steps"], b["steps"])
     assert b["exact_tests"] > a["exact_tests"]
+
+
+def test_fast_turning_point_equals_bisection_and_reference():
+    """solve_turning_point (closed form + Newton + grid tests) must return what the 20-step bisection
+    returns -- the kernel's literal copy of it AND the reference's StaticBlackhole::SolveG (via the C
+    oracle) -- for impact parameters from b_c up to far field, including values next to b_c."""
+    L = harness()
+    rng = np.random.default_rng(8)
+    for M in (10.0, 20.0, 1.0, 3.7):
+        b_c = 3.0 * np.sqrt(3.0) * M
+        b = np.concatenate([
+            b_c * (1.0 + np.logspace(-13, 2.5, 4000)),
+            b_c * (1.0 + rng.random(4000) * 0.01),
+            b_c * (1.0 + rng.random(20000) * 60.0),
+            [b_c, np.nextafter(b_c, np.inf), 1e6 * M],
+        ])
+        fast = np.empty_like(b)
+        bis = np.empty_like(b)
+        L.bh8_harness_solve(C.c_double(M), b.ctypes.data_as(C.c_void_p), C.c_int(len(b)),
+                            fast.ctypes.data_as(C.c_void_p), bis.ctypes.data_as(C.c_void_p))
+        ref = np.array([O.lib().bh8_oracle_solve_g(M, float(x)) for x in b])
+        grid = (1.0 / (3 * M) - np.cbrt(np.finfo(float).eps)) / 2 ** 20
+        assert np.all(np.abs(bis - ref) <= 1e-3 * grid)   # the kernel's bisection == the reference's
+        bad = np.abs(fast - bis) > 1e-3 * grid
+        assert bad.sum() == 0, (M, b[bad][:5], fast[bad][:5], bis[bad][:5])
+
+
+def test_sincos_primitive_is_within_one_ulp():
+    L = harness()
+    rng = np.random.default_rng(3)
+    x = np.concatenate([(rng.random(2_000_000) - 0.3) * 200.0, (rng.random(200_000) - 0.5) * 2.0,
+                        np.arange(-60, 61) * (np.pi / 4), [0.0, 1e-300, -1e-9]])
+    s = np.empty_like(x)
+    c = np.empty_like(x)
+    L.bh8_harness_sincos(x.ctypes.data_as(C.c_void_p), C.c_int(len(x)), s.ctypes.data_as(C.c_void_p),
+                         c.ctypes.data_as(C.c_void_p))
+    assert np.abs(s - np.sin(x)).max() <= 2.3e-16
+    assert np.abs(c - np.cos(x)).max() <= 2.3e-16
