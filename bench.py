@@ -54,13 +54,14 @@ def load_texture(name):
     return np.ascontiguousarray(img)
 
 
-def flythrough_snapshots(n_frames=240):
-    """Frames of BASELINE configs[3]: the per-frame camera / disc states the reference's own classes
-    produce when its frame loop is replayed (tools/make_flythrough.py -> tests/golden/states/cfg3_flythrough.json;
-    'w' MoveX(+10) for frames 0-119, then 'L' RotateZ(pi/180) + 'd' MoveY(+10), disc RotateZ(pi/180)
-    every frame: blackhole_solution_test.cc:346-407)."""
+def frame_sequence(which, n_frames=240):
+    """Consecutive frames as the reference's frame loop produces them (blackhole_solution_test.cc:346-407),
+    snapshotted from the reference's own classes by tools/make_flythrough.py:
+      "cfg1_spin"        configs[1]: fixed camera, the disc spins RotateZ(pi/180) after every frame (:407)
+      "cfg3_flythrough"  configs[3]: 'w' MoveX(+10) for frames 0-119, then 'L' RotateZ(pi/180) + 'd'
+                         MoveY(+10), plus the disc spin."""
     from blackhole_8_b200 import abi
-    with open(os.path.join(ROOT, "tests", "golden", "states", "cfg3_flythrough.json")) as f:
+    with open(os.path.join(ROOT, "tests", "golden", "states", which + ".json")) as f:
         fly = json.load(f)
     out = []
     for fr in fly["frames"][:n_frames]:
@@ -115,6 +116,37 @@ class ClockSampler(threading.Thread):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def ncu_summary():
+    """Hardware view of the same kernel from the newest committed ncu capture (profiles/*_ncu_render_kernel_summary.txt):
+    FP64 pipe utilisation, issue-slot utilisation, lanes per instruction, registers.  Static context for the
+    live roofline numbers, never a substitute for them."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_render_kernel_summary.txt")))
+    if not files:
+        return None
+    want = {"sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed": "fp64_pipe_active_pct",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_active_pct",
+            "smsp__thread_inst_executed_per_inst_executed.ratio": "threads_per_instruction",
+            "smsp__sass_average_branch_targets_threads_uniform.pct": "uniform_branch_targets_pct",
+            "launch__registers_per_thread": "registers_per_thread",
+            "sm__warps_active.avg.per_cycle_active": "warps_per_sm",
+            "gpu__time_duration.sum": "kernel_us_under_ncu"}
+    out = {"source": os.path.relpath(files[-1], ROOT)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    dram = 0.0
+    for line in open(files[-1]):
+        m = re.match(r"(\S+) \[(.*)\] = ([-0-9.e+]+)", line)
+        if not m:
+            continue
+        if m.group(1) in want:
+            out[want[m.group(1)]] = float(m.group(3))
+        if m.group(1) in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            dram += float(m.group(3)) * scale.get(m.group(2), 1.0)
+    out["dram_bytes_per_launch"] = dram
+    return out
 
 
 def host_threads():
@@ -187,6 +219,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batching", action="store_true")
+    ap.add_argument("--workload", default="cfg1_spin", choices=["cfg1_spin", "cfg3_flythrough", "cfg1_static"],
+                    help="frame sequence: configs[1] with the disc spinning frame to frame as in the "
+                         "reference's loop (default), the configs[3] fly-through, or configs[1] frame 0 only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,6 +243,7 @@ def main():
     args.warmup = max(args.warmup, 3)
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     base = load_snapshot()
@@ -217,14 +253,16 @@ def main():
     r.set_textures(base, load_texture)
     flags = abi.FLAG_NO_BATCHING if args.no_batching else 0
 
-    # frames this rank renders: N == 1 -> the configs[1] frame every step; N > 1 -> fly-through frames
-    if world > 1:
-        from blackhole_8_b200 import sharding
-        fly = flythrough_snapshots(240)
-        # step i of the job renders frames i*world .. i*world+world-1; rank r owns frame i*world + r
-        my_frames = [fly[k % 240] for k in sharding.frames_of((args.steps + args.warmup) * world, rank, world)]
+    # Frames are whole units of work: step i of the job renders frames i*world .. i*world+world-1 of
+    # the sequence and rank r owns frame i*world + r (sharding.frames_of) -- the same workload at every
+    # N, no data-path collective.
+    from blackhole_8_b200 import sharding
+    if args.workload == "cfg1_static":
+        seq = [base]
     else:
-        my_frames = [base] * (args.steps + args.warmup)
+        seq = frame_sequence(args.workload, 240)
+    my_frames = [seq[k % len(seq)] for k in
+                 sharding.frames_of((args.steps + args.warmup + 3) * world, rank, world)]
 
     # ---- device-resident frame ring on GPU 0 (peer-mapped into the other ranks) ----------------
     frame_bytes = rays * 4
@@ -246,10 +284,20 @@ def main():
         from blackhole_8_b200 import sharding
         return ring + sharding.ring_slot_offset(step, rank, world, ring_slots, frame_bytes)
 
-    # one untimed launch with counters: steps / class mix of this rank's first frame
-    r.render_device(my_frames[0], slot_ptr(0), flags=flags | abi.FLAG_STATS)
+    # untimed pass with the device counters on: geodesic steps / class mix of exactly the frames the
+    # timed region renders (they feed steps/s and the algorithmic flop count)
+    for i in range(args.steps):
+        r.render_device(my_frames[args.warmup + i], slot_ptr(i), flags=flags | abi.FLAG_STATS)
     r.sync()
-    st = r.read_stats()
+    st_raw = r.read_stats()
+    cnt = torch.tensor([st_raw.rays, st_raw.steps] + list(st_raw.class_count), dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cnt)
+    cnt = [float(x) / args.steps for x in cnt.tolist()]  # per step, summed over ranks
+
+    class _St:
+        rays, steps, class_count = cnt[0], cnt[1], cnt[2:6]
+    st = _St
     launches0 = r.launches
 
     for i in range(args.warmup):
@@ -331,9 +379,10 @@ def main():
 
     # ---- roofline: algorithmic FP64 flops / kernel time vs the DFMA peak measured now ----------
     n_extra = max(0, base.scene.n_obj - 2)
-    hits = int(st.rays - st.class_count[0])
-    flops_frame = (FLOPS_PER_STEP_BASE + FLOPS_PER_EXTRA_OBJECT * n_extra) * st.steps + FLOPS_SETUP * st.rays + \
-        FLOPS_TERMINAL * hits
+    hits = st.rays - st.class_count[0]
+    # per step of the whole job (all ranks); one launch = one rank's frame = 1/world of it
+    flops_frame = ((FLOPS_PER_STEP_BASE + FLOPS_PER_EXTRA_OBJECT * n_extra) * st.steps + FLOPS_SETUP * st.rays +
+                   FLOPS_TERMINAL * hits) / world
     peak, _ = r.measure_fp64_peak()
     achieved = flops_frame / (ms_per_step * 1e-3)
     roofline = {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
@@ -344,6 +393,10 @@ def main():
                 "convention": "SURVEY 8(d) W_sm100: %d flops/geodesic step, 385/ray setup, 130/terminal hit"
                               % (FLOPS_PER_STEP_BASE + FLOPS_PER_EXTRA_OBJECT * n_extra)}
 
+    ncu = ncu_summary()
+    if ncu:
+        roofline["traffic"] = ncu.pop("dram_bytes_per_launch", None)  # bytes/launch from the ncu capture
+        roofline["pipe_utilisation"] = ncu
     cpu = None
     if not args.no_cpu_baseline:
         threads = host_threads()
@@ -361,15 +414,17 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg1: 1 Schwarzschild BH + accretion disc (acc_disc.png) + background rectangle, "
                                "1920x1080, nstep 20, one frame per step" +
-                               ("; N>1: every rank renders its own fly-through frame (cfg3) per step into GPU 0's "
-                                "IPC-mapped frame ring" if world > 1 else ""),
+                               "; frame sequence '%s' (the reference's frame loop: disc spins pi/180 per frame)" % args.workload +
+                               ("; rank r renders frame i*N+r of the sequence at step i into GPU 0's IPC-mapped frame "
+                                "ring (NVLink peer stores, no collective)" if world > 1 else ""),
                    "rays_per_step": rays * world, "steps_per_ray": st.steps / st.rays,
+                   "geodesic_steps_per_step": st.steps,
                    "class_mix": {"background": st.class_count[0] / st.rays, "horizon": st.class_count[1] / st.rays,
                                  "disc": st.class_count[2] / st.rays, "object": st.class_count[3] / st.rays},
                    "l2": "flushed between steps by a 256 MiB memset outside the per-step CUDA-event pair",
                    "batched_resolve": not args.no_batching},
         "frames_per_s": world * 1e3 / ms_per_step,
-        "gsteps_per_s": st.steps * world / (ms_per_step * 1e-3) / 1e9,
+        "gsteps_per_s": st.steps / (ms_per_step * 1e-3) / 1e9,
         "wall_s_timed_region": wall_s,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 8192 * world,

@@ -15,13 +15,11 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 REF = os.path.join(ROOT, "oracle", "_ref", "ref_render")
 
 
-def main():
-    if not os.path.exists(REF):
-        sys.exit("oracle/_ref/ref_render missing: run `make -C oracle ref`")
+def states(cfg, name):
     frames = []
     base = None
     for k in range(240):
-        out = subprocess.run([REF, "--cfg", "3", "--width", "1920", "--height", "1080", "--frame", str(k),
+        out = subprocess.run([REF, "--cfg", str(cfg), "--width", "1920", "--height", "1080", "--frame", str(k),
                               "--snapshot-only", "--texdir", os.path.join(ROOT, "build", "textures")],
                              check=True, capture_output=True, text=True).stdout
         d = json.loads(out)
@@ -30,9 +28,16 @@ def main():
         frames.append({"camera": {k2: d["camera"][k2] for k2 in ("pos", "vx", "vy", "vz")},
                        "v": [o["v"] for o in d["objects"]]})
     base.pop("run", None)
-    with open(os.path.join(ROOT, "tests", "golden", "states", "cfg3_flythrough.json"), "w") as f:
+    with open(os.path.join(ROOT, "tests", "golden", "states", name), "w") as f:
         json.dump({"base": base, "frames": frames}, f)
-    print("wrote %d frames" % len(frames))
+    print("wrote %d frames to %s" % (len(frames), name))
+
+
+def main():
+    if not os.path.exists(REF):
+        sys.exit("oracle/_ref/ref_render missing: run `make -C oracle ref`")
+    states(3, "cfg3_flythrough.json")  # camera script + disc spin
+    states(1, "cfg1_spin.json")        # cfg 1 as the reference's frame loop shows it: disc RotateZ(pi/180) per frame
 
 
 if __name__ == "__main__":
