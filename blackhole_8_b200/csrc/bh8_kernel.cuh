@@ -66,9 +66,10 @@ struct DeviceFetch {
 // Mailbox, stride kThreads.  doubles: [0..2] e2 (hit point once the ray has ended), [3] u, [4] phi,
 // [5] dphi_prev, [6] delta, [7] phi_trig, [8] t, [9] du_h, [10] binv2.  ints: [0] i, [1] next_evt,
 // [2] state, [3] fbits, [4] fstep, [5] steps, [6] hit_obj, [7] flags, [8] gate_in, [9] gate_out,
-// [10..] fa/fb bit patterns.  Slots from du_h / flags on never change after setup: written once.
+// [10] lo, [11] span, [12..] fa/fb bit patterns.  du_h, binv2, flags, gates, lo, fa/fb never change
+// after setup: written once.
 constexpr int kMailDoubles = 11;
-constexpr int kMailInts = 10 + 2 * kMaxFilterPlanes;
+constexpr int kMailInts = 12 + 2 * kMaxFilterPlanes;
 
 template <int NN>
 __device__ __forceinline__ void lane_park_constants(const Lane<NN>& L, volatile double* md, volatile int* mi) {
@@ -77,10 +78,11 @@ __device__ __forceinline__ void lane_park_constants(const Lane<NN>& L, volatile 
   mi[7 * kThreads] = L.flags;
   mi[8 * kThreads] = L.gate_in;
   mi[9 * kThreads] = L.gate_out;
+  mi[10 * kThreads] = L.lo;
 #pragma unroll
   for (int j = 0; j < (NN > 0 ? NN : 0); ++j) {
-    mi[(10 + 2 * j) * kThreads] = __float_as_int(L.fa[j]);
-    mi[(11 + 2 * j) * kThreads] = __float_as_int(L.fb[j]);
+    mi[(12 + 2 * j) * kThreads] = __float_as_int(L.fa[j]);
+    mi[(13 + 2 * j) * kThreads] = __float_as_int(L.fb[j]);
   }
 }
 
@@ -99,6 +101,7 @@ __device__ __forceinline__ void lane_park(const Lane<NN>& L, volatile double* md
   mi[4 * kThreads] = L.fstep;
   mi[5 * kThreads] = L.steps;
   mi[6 * kThreads] = L.hit_obj;
+  mi[11 * kThreads] = (int)L.span;
 }
 
 template <int NN>
@@ -121,10 +124,12 @@ __device__ __forceinline__ void lane_unpark(Lane<NN>& L, const volatile double* 
   L.flags = mi[7 * kThreads];
   L.gate_in = mi[8 * kThreads];
   L.gate_out = mi[9 * kThreads];
+  L.lo = mi[10 * kThreads];
+  L.span = (uint32_t)mi[11 * kThreads];
 #pragma unroll
   for (int j = 0; j < (NN > 0 ? NN : 0); ++j) {
-    L.fa[j] = __int_as_float(mi[(10 + 2 * j) * kThreads]);
-    L.fb[j] = __int_as_float(mi[(11 + 2 * j) * kThreads]);
+    L.fa[j] = __int_as_float(mi[(12 + 2 * j) * kThreads]);
+    L.fb[j] = __int_as_float(mi[(13 + 2 * j) * kThreads]);
   }
   L.bgr = 0;
   L.oob = 0;

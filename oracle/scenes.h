@@ -14,6 +14,10 @@
 //   cfg 3  fly-through frame k of cfg 1 (disc spin blackhole_solution_test.cc:407, camera script in
 //          the reference's key actions :346-389)
 //   cfg 4  cfg 1 scene at nstep 200
+//   cfg 6-9  stress scenes for the GPU path's rarely taken branches (not BASELINE configs):
+//          6 hole moved off the disc's plane (arrow keys, blackhole_solution_test.cc:391-396) and
+//            camera tilted; 7 camera turned away from the hole (mirrored-start rays, the atan quirk);
+//          8 more planes than the kernel has filter slots; 9 camera inside the photon sphere
 //
 // Because ObjectManager is a leaked singleton without enumeration (object_manager.h:30-33,92) the
 // builder keeps its own list of what it inserted, in insertion order.
@@ -157,6 +161,45 @@ inline Scene* Build(int cfg, int width, int height, int frame, const std::string
       AddRectangle(s, m, texdir, "winter.jpg", -100, 50, 100, -100, -50, 100, -100, -50, 0, -100, 50, 0);
       AddChess(s, m, 10);
       AddBlackhole(s, m, 20);
+      break;
+    case 6:  // hole off the disc plane: the disc and the rectangle are both "non-central"
+      s = new Scene(width, height, blackhole::pi / 2);
+      s->camera.MoveTo(-2000, 0, 400);
+      s->camera.RotateY(0.1);
+      AddDisc(s, m, texdir);
+      AddBackground(s, m, texdir);
+      AddBlackhole(s, m, 10);
+      for (int k = 0; k < 10; ++k) s->blackhole->MoveZ(5);   // kUp x10
+      for (int k = 0; k < 6; ++k) s->blackhole->MoveY(-5);   // kRight x6
+      break;
+    case 7:  // camera looks mostly away from the hole: F.pv > F.F for many pixels
+      s = new Scene(width, height, blackhole::pi / 2);
+      s->camera.MoveTo(-300, 40, 120);
+      s->camera.RotateZ(2.2);
+      AddDisc(s, m, texdir);
+      AddBackground(s, m, texdir);
+      AddBlackhole(s, m, 10);
+      break;
+    case 8:  // seven planes that do not contain the hole's centre + the chess floor + the disc
+      s = new Scene(width, height, blackhole::pi / 2);
+      s->camera.MoveTo(-900, 150, 260);
+      AddDisc(s, m, texdir);
+      AddBackground(s, m, texdir);
+      AddRectangle(s, m, texdir, "mooni.jpeg", 100, 253, 199, 100, 0, 199, 100, 0, 0, 100, 253, 0);
+      AddRectangle(s, m, texdir, "karina.jpeg", 100, 0, 300, 100, -200, 300, 100, -200, 0, 100, 0, 0);
+      AddRectangle(s, m, texdir, "winter.jpg", -100, 50, 100, -100, -50, 100, -100, -50, 0, -100, 50, 0);
+      AddRectangle(s, m, texdir, "mooni.jpeg", -400, 300, 350, -400, 100, 350, -400, 100, 150, -400, 300, 150);
+      AddRectangle(s, m, texdir, "winter.jpg", 300, -300, 500, 300, -600, 500, 300, -600, 200, 300, -300, 200);
+      AddRectangle(s, m, texdir, "karina.jpeg", -200, -400, 300, 0, -400, 300, 0, -400, 0, -200, -400, 0);
+      AddChess(s, m, 25);
+      AddBlackhole(s, m, 10);
+      break;
+    case 9:  // camera at r = 25.5 < 3M: du < 0, every segment takes the exact path
+      s = new Scene(width, height, blackhole::pi / 2);
+      s->camera.MoveTo(-25, 0, 5);
+      AddDisc(s, m, texdir);
+      AddBackground(s, m, texdir);
+      AddBlackhole(s, m, 10);
       break;
     default:
       return nullptr;

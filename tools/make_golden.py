@@ -35,6 +35,13 @@ SMALL = {
     "cfg3_frame180_480x270": (3, 480, 270, 180, None),
     "cfg4_nstep200_320x180": (4, 320, 180, 0, None),
     "cfg1_odd_333x187": (1, 333, 187, 0, None),  # ragged size: not a multiple of any tile
+    # stress scenes (oracle/scenes.h cfg 6-9): the GPU path's rarely taken branches
+    "cfg6_offplane_400x225": (6, 400, 225, 0, None),
+    "cfg7_lookaway_400x225": (7, 400, 225, 0, None),
+    "cfg8_manyplanes_400x225": (8, 400, 225, 0, None),
+    "cfg9_inside_320x180": (9, 320, 180, 0, None),
+    "cfg1_nstep2_320x180": (1, 320, 180, 0, 2),
+    "cfg1_tiny_5x3": (1, 5, 3, 0, None),
 }
 DIGEST_ONLY = {
     "cfg1_1920x1080": (1, 1920, 1080, 0, None),
