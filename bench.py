@@ -427,7 +427,7 @@ def main():
         "gsteps_per_s": st.steps / (ms_per_step * 1e-3) / 1e9,
         "wall_s_timed_region": wall_s,
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 8192 * world,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(r.lib.bh8_launch_param_bytes()) * world,
                 "d2h_bytes_per_step": frame_bytes * world, "steps": e2e_steps,
                 "frames_per_s": world * e2e_steps / e2e_s, "frame_ok": frame_ok,
                 "what": "bh8_submit()/bh8_wait(): snapshot -> kernel parameters, RGBA8 frame read back into pinned "

@@ -179,6 +179,8 @@ int bh8_abi_version(void) { return BH8_ABI_VERSION; }
 
 size_t bh8_pixel_bytes(int pixel_format) { return pixel_format == BH8_PIXEL_BGR8 ? 3 : 4; }
 
+size_t bh8_launch_param_bytes(void) { return sizeof(Bh8Frame) + sizeof(bh8::Bh8Tex) + sizeof(bh8::Bh8Out); }
+
 const char* bh8_last_error(const bh8_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 uint64_t bh8_launch_count(const bh8_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -36,6 +36,7 @@ def load_library(path=None):
     sig = {
         "bh8_abi_version": (i32, []),
         "bh8_pixel_bytes": (C.c_size_t, [i32]),
+        "bh8_launch_param_bytes": (C.c_size_t, []),
         "bh8_create": (i32, [C.POINTER(vp), C.POINTER(C.c_int), i32]),
         "bh8_destroy": (None, [vp]),
         "bh8_last_error": (C.c_char_p, [vp]),

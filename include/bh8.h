@@ -200,6 +200,9 @@ int bh8_memset_d(bh8_ctx* ctx, void* d_ptr, int value, size_t bytes);
 int bh8_measure_fp64_peak(bh8_ctx* ctx, double* flops_per_s, double* seconds_run);
 
 size_t bh8_pixel_bytes(int pixel_format);
+/* Bytes that travel host -> device per frame: the frame constants derived from the snapshot, passed as
+ * kernel parameters (there is no other per-frame input). */
+size_t bh8_launch_param_bytes(void);
 
 #ifdef __cplusplus
 }

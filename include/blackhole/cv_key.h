@@ -1,18 +1,6 @@
-// blackhole/cv_key.h -- cv::waitKeyEx codes the interactive drivers react to (macOS values, as in
-// the reference's cv_key.h:10-16).
-#ifndef BLACKHOLE_CV_KEY_H_
-#define BLACKHOLE_CV_KEY_H_
-
-namespace blackhole {
-
-enum Key {
-  kEscape = 27,
-  kUp = 63232,
-  kDown = 63233,
-  kLeft = 63234,
-  kRight = 63235,
-};
-
-}  // namespace blackhole
-
-#endif  // BLACKHOLE_CV_KEY_H_
+// Forwarding header: the reference's include path blackhole/cv_key.h maps onto this repository's
+// implementation in blackhole/core/.
+#ifndef BH8_FWD_CV_KEY_H_
+#define BH8_FWD_CV_KEY_H_
+#include "blackhole/core/environment.h"
+#endif  // BH8_FWD_CV_KEY_H_

@@ -1,4 +1,5 @@
-// blackhole/object/polygon_object.h -- placeholder, empty in the reference as well.
-#ifndef BLACKHOLE_POLYGON_OBJECT_H_
-#define BLACKHOLE_POLYGON_OBJECT_H_
-#endif  // BLACKHOLE_POLYGON_OBJECT_H_
+// Forwarding header: the reference's include path blackhole/object/polygon_object.h maps onto this repository's
+// implementation in blackhole/core/.
+#ifndef BH8_FWD_OBJECT_POLYGON_OBJECT_H_
+#define BH8_FWD_OBJECT_POLYGON_OBJECT_H_
+#endif  // BH8_FWD_OBJECT_POLYGON_OBJECT_H_
