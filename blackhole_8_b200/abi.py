@@ -8,7 +8,7 @@ import json
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_OBJECTS = 16
 MAX_TEXTURES = 16
 
@@ -17,6 +17,7 @@ CLASS_BACKGROUND, CLASS_HORIZON, CLASS_DISC, CLASS_OBJECT = 0, 1, 2, 3
 PATTERN_BLACK, PATTERN_CHESS = 0, 1
 PIXEL_RGBA8, PIXEL_BGRA8, PIXEL_BGR8 = 0, 1, 2
 FLAG_STATS, FLAG_NO_BATCHING = 1, 2
+TRACER_GEODESIC, TRACER_LINEAR = 0, 1
 
 EINVAL, EUNSUPPORTED, ECUDA, ENOMEM, ENODEVICE = -1, -2, -3, -4, -5
 
@@ -68,6 +69,8 @@ class Params(C.Structure):
         ("stripe_rows", C.c_int32),
         ("shard_index", C.c_int32),
         ("shard_count", C.c_int32),
+        ("tracer", C.c_int32),
+        ("linear_steps", C.c_int32),
     ]
 
 
@@ -93,13 +96,19 @@ class SceneSnapshot:
     snapshot helper writes; `textures` lists the reference resource names by texture slot.
     """
 
-    def __init__(self, camera, objects, bh_index, textures=(), nstep=20, meta=None):
+    def __init__(self, camera, objects, bh_index, textures=(), nstep=20, meta=None, linear_steps=0):
         self.camera = camera
         self.objects = (Object * len(objects))(*objects)
         self.scene = Scene(len(objects), bh_index, C.cast(self.objects, C.POINTER(Object)))
         self.textures = list(textures)
         self.nstep = nstep
+        self.linear_steps = linear_steps  # > 0: flat-space scene (RayTracer::Prograde), no black hole needed
         self.meta = meta or {}
+
+    def params(self, pixel_format=PIXEL_RGBA8, flags=0, nstep=None, stripe_rows=0, shard_index=0, shard_count=0):
+        """bh8_params for this snapshot: geodesic tracer, or the linear one for a flat-space scene."""
+        return Params(nstep or self.nstep, pixel_format, flags, stripe_rows, shard_index, shard_count,
+                      TRACER_LINEAR if self.linear_steps > 0 else TRACER_GEODESIC, self.linear_steps)
 
     @property
     def width(self):
@@ -122,7 +131,8 @@ class SceneSnapshot:
                                Vec3(*o["ex"]), Vec3(*o["ey"]), o["r_in"], o["r_out"], o["mass"],
                                o["pattern_size"]))
         meta = {k: d[k] for k in ("cfg", "frame", "run") if k in d}
-        return cls(cam, objs, d["bh_index"], d.get("textures", ()), d.get("nstep", 20), meta)
+        return cls(cam, objs, d["bh_index"], d.get("textures", ()), d.get("nstep", 20), meta,
+                   d.get("linear_steps", 0))
 
     @classmethod
     def from_json(cls, path):
@@ -140,7 +150,7 @@ class SceneSnapshot:
                 "pattern_size": o.pattern_size,
             })
         return {
-            "nstep": self.nstep, "width": c.width, "height": c.height,
+            "nstep": self.nstep, "linear_steps": self.linear_steps, "width": c.width, "height": c.height,
             "camera": {"pos": list(c.pos), "vx": list(c.vx), "vy": list(c.vy), "vz": list(c.vz),
                        "focus_len": c.focus_len, "width": c.width, "height": c.height},
             "textures": list(self.textures), "bh_index": self.scene.bh_index, "objects": objs,

@@ -53,6 +53,7 @@ struct Bh8Frame {
   double nine_m2;         // (3M)^2: q = nine_m2 / b^2 is the constant term of the normalised cubic
   // integration
   int32_t nstep, n_obj, bh_index, n_central;
+  int32_t tracer, linear_steps;  // BH8_TRACER_*; segments per ray of the linear tracer
   double inv_nstep;
   // conservative filters (see bh8_ray.cuh)
   double u_gate;        // non-central planes can only be crossed while min(u) <= u_gate
@@ -101,14 +102,22 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
   } while (0)
   if (!scene || !cam || !prm || !scene->obj) BH8_FAIL(BH8_EINVAL, "null scene / camera / params");
   if (scene->n_obj < 1 || scene->n_obj > BH8_MAX_OBJECTS) BH8_FAIL(BH8_EINVAL, "n_obj out of range");
-  if (scene->bh_index < 0 || scene->bh_index >= scene->n_obj ||
-      scene->obj[scene->bh_index].kind != BH8_KIND_BLACKHOLE)
+  const bool linear = prm->tracer == BH8_TRACER_LINEAR;
+  if (prm->tracer != BH8_TRACER_GEODESIC && !linear) BH8_FAIL(BH8_EINVAL, "unknown tracer");
+  if (linear && (prm->linear_steps < 1 || prm->linear_steps > 65535))
+    BH8_FAIL(BH8_EINVAL, "linear_steps must be in [1, 65535]");
+  // The geodesic tracer bends rays around obj[bh_index]; the linear one needs no hole (bh_index may
+  // be -1), and a StaticBlackhole in a flat-space scene is just a black sphere to FindCollision.
+  if (!(linear && scene->bh_index == -1) &&
+      (scene->bh_index < 0 || scene->bh_index >= scene->n_obj ||
+       scene->obj[scene->bh_index].kind != BH8_KIND_BLACKHOLE))
     BH8_FAIL(BH8_EINVAL, "bh_index does not name a BH8_KIND_BLACKHOLE object");
   if (cam->width < 1 || cam->height < 1 || cam->width > 65536 || cam->height > 65536)
     BH8_FAIL(BH8_EINVAL, "camera size out of range");
-  if (prm->nstep < 2 || prm->nstep > 32767) BH8_FAIL(BH8_EINVAL, "nstep must be in [2, 32767]");
+  if (!linear && (prm->nstep < 2 || prm->nstep > 32767)) BH8_FAIL(BH8_EINVAL, "nstep must be in [2, 32767]");
   if (prm->pixel_format < 0 || prm->pixel_format > BH8_PIXEL_BGR8) BH8_FAIL(BH8_EINVAL, "bad pixel_format");
-  const bh8_object* bho = &scene->obj[scene->bh_index];
+  static const bh8_object kNoHole = {BH8_KIND_BLACKHOLE, -1, -1, 0, {{0}}, {0}, {0}, {0}, 0, 0, 1.0, 0};
+  const bh8_object* bho = scene->bh_index >= 0 ? &scene->obj[scene->bh_index] : &kNoHole;
   if (!(bho->mass > 0)) BH8_FAIL(BH8_EINVAL, "black hole mass must be positive");
 
   memset(f, 0, sizeof *f);
@@ -150,8 +159,10 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
       f->bis_h[i] = h;  // bis_h[i] = (r-l)/2^(i+2)
     }
   }
-  f->nstep = prm->nstep;
-  f->inv_nstep = 1.0 / prm->nstep;
+  f->tracer = prm->tracer;
+  f->linear_steps = prm->linear_steps;
+  f->nstep = linear ? 2 : prm->nstep;
+  f->inv_nstep = 1.0 / f->nstep;
   f->n_obj = scene->n_obj;
   f->bh_index = scene->bh_index;
   f->pixel_format = prm->pixel_format;

@@ -135,6 +135,65 @@ __device__ __forceinline__ void lane_unpark(Lane<NN>& L, const volatile double* 
   L.oob = 0;
 }
 
+// Pixel store + optional maps + optional counters, shared by both kernels.  RGBA8 / BGRA8 go through
+// a shared tile and leave as 16-byte coalesced stores (4 pixels per store, 128 B per tile row).
+__device__ __forceinline__ void store_pixel(const Bh8Frame& f, const Bh8Out& out, uint32_t* sh_rgba,
+                                            unsigned long long* sh_red, int tid, int lane, int slot, int x0,
+                                            int y0, int x, int y, bool inside, uint32_t bgr, uint32_t oob,
+                                            int cls, int key, int steps) {
+  const size_t gi = (size_t)y * f.width + x;
+  if (f.pixel_format == BH8_PIXEL_BGR8) {
+    if (inside) {
+      uint8_t* d = out.pixels + gi * 3;
+      d[0] = (uint8_t)bgr;
+      d[1] = (uint8_t)(bgr >> 8);
+      d[2] = (uint8_t)(bgr >> 16);
+    }
+  } else {
+    const uint32_t px4 = (f.pixel_format == BH8_PIXEL_BGRA8)
+                             ? (bgr | 0xFF000000u)
+                             : (((bgr >> 16) & 0xFFu) | (bgr & 0xFF00u) | ((bgr & 0xFFu) << 16) | 0xFF000000u);
+    if (out.vec_ok) {
+      sh_rgba[slot] = px4;
+      __syncthreads();
+      if (tid < kThreads / 4) {
+        const int row = tid >> 3, col = (tid & 7) * 4;
+        if (x0 + col < f.width && y0 + row < f.height) {
+          const uint4 v = *reinterpret_cast<const uint4*>(&sh_rgba[row * kTileW + col]);
+          *reinterpret_cast<uint4*>(out.pixels + ((size_t)(y0 + row) * f.width + x0 + col) * 4) = v;
+        }
+      }
+    } else if (inside) {
+      reinterpret_cast<uint32_t*>(out.pixels)[gi] = px4;
+    }
+  }
+  if (inside) {
+    if (out.cls) out.cls[gi] = (uint8_t)cls;
+    if (out.key) out.key[gi] = (int8_t)key;
+    if (out.steps) out.steps[gi] = (uint16_t)steps;
+  }
+
+  // ---- optional counters ----------------------------------------------------------------------------
+  if (f.flags & BH8_FLAG_STATS) {
+    if (tid < 7) sh_red[tid] = 0ull;
+    __syncthreads();
+    unsigned long long v[7];
+    v[0] = inside ? 1ull : 0ull;
+    v[1] = inside ? (unsigned long long)steps : 0ull;
+    for (int k = 0; k < 4; ++k) v[2 + k] = (inside && cls == k) ? 1ull : 0ull;
+    v[6] = oob;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      unsigned long long s = v[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0 && s) atomicAdd(&sh_red[k], s);
+    }
+    __syncthreads();
+    if (tid < 7 && sh_red[tid]) atomicAdd(&out.stats[tid], sh_red[tid]);
+  }
+}
+
 template <int NN>
 __global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
 bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
@@ -219,57 +278,45 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
     cls = f.obj[L.hit_obj].cls;
     key = f.obj[L.hit_obj].key;
   }
-  const size_t gi = (size_t)y * f.width + x;
-  if (f.pixel_format == BH8_PIXEL_BGR8) {
-    if (inside) {
-      uint8_t* d = out.pixels + gi * 3;
-      d[0] = (uint8_t)bgr;
-      d[1] = (uint8_t)(bgr >> 8);
-      d[2] = (uint8_t)(bgr >> 16);
-    }
-  } else {
-    const uint32_t px4 = (f.pixel_format == BH8_PIXEL_BGRA8)
-                             ? (bgr | 0xFF000000u)
-                             : (((bgr >> 16) & 0xFFu) | (bgr & 0xFF00u) | ((bgr & 0xFFu) << 16) | 0xFF000000u);
-    if (out.vec_ok) {
-      sh_rgba[slot] = px4;
-      __syncthreads();
-      if (tid < kThreads / 4) {
-        const int row = tid >> 3, col = (tid & 7) * 4;
-        if (x0 + col < f.width && y0 + row < f.height) {
-          const uint4 v = *reinterpret_cast<const uint4*>(&sh_rgba[row * kTileW + col]);
-          *reinterpret_cast<uint4*>(out.pixels + ((size_t)(y0 + row) * f.width + x0 + col) * 4) = v;
-        }
-      }
-    } else if (inside) {
-      reinterpret_cast<uint32_t*>(out.pixels)[gi] = px4;
-    }
-  }
-  if (inside) {
-    if (out.cls) out.cls[gi] = (uint8_t)cls;
-    if (out.key) out.key[gi] = (int8_t)key;
-    if (out.steps) out.steps[gi] = (uint16_t)steps;
-  }
+  store_pixel(f, out, sh_rgba, sh_red, tid, lane, slot, x0, y0, x, y, inside, bgr, oob, cls, key, steps);
+}
 
-  // ---- optional counters ----------------------------------------------------------------------------
-  if (f.flags & BH8_FLAG_STATS) {
-    if (tid < 7) sh_red[tid] = 0ull;
-    __syncthreads();
-    unsigned long long v[7];
-    v[0] = inside ? 1ull : 0ull;
-    v[1] = inside ? (unsigned long long)steps : 0ull;
-    for (int k = 0; k < 4; ++k) v[2 + k] = (inside && cls == k) ? 1ull : 0ull;
-    v[6] = oob;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      unsigned long long s = v[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0 && s) atomicAdd(&sh_red[k], s);
-    }
-    __syncthreads();
-    if (tid < 7 && sh_red[tid]) atomicAdd(&out.stats[tid], sh_red[tid]);
+// Flat-space tracer (BH8_TRACER_LINEAR): one thread per pixel, at most linear_steps segment tests,
+// same tile mapping, colour and store path as the geodesic kernel.
+__global__ void __launch_bounds__(kThreads, 4)
+bh8_linear_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
+  __shared__ __align__(16) uint32_t sh_rgba[kThreads];
+  __shared__ unsigned long long sh_red[7];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.x * kTileW;
+  int y0;
+  if (f.shard_count > 1) {
+    const int tiles_per_stripe = f.stripe_rows / kTileH;
+    const int ls = blockIdx.y / tiles_per_stripe;
+    const int within = blockIdx.y - ls * tiles_per_stripe;
+    y0 = (ls * f.shard_count + f.shard_index) * f.stripe_rows + within * kTileH;
+  } else {
+    y0 = blockIdx.y * kTileH;
   }
+  if (y0 >= f.height) return;
+  const int px = (warp & 3) * 8 + (lane & 7);
+  const int py = (warp >> 2) * 4 + (lane >> 3);
+  const int slot = py * kTileW + px;
+  const int x = x0 + px, y = y0 + py;
+  const bool inside = x < f.width && y < f.height;
+
+  int hit = -1, steps = 0;
+  double hp[3] = {0.0, 0.0, 0.0};
+  if (inside) steps = trace_linear(f, x, y, &hit, hp);
+  uint32_t bgr = 0, oob = 0;
+  int cls = BH8_CLASS_BACKGROUND, key = -1;
+  if (hit >= 0) {
+    bgr = shade(f, hit, hp, DeviceFetch{tex}, &oob);
+    cls = f.obj[hit].cls;
+    key = f.obj[hit].key;
+  }
+  store_pixel(f, out, sh_rgba, sh_red, tid, lane, slot, x0, y0, x, y, inside, bgr, oob, cls, key, steps);
 }
 
 // FP64 pipe peak: 8 independent DFMA chains per thread, enough warps to fill every SM.

@@ -117,6 +117,12 @@ int launch_frame(bh8_ctx* ctx, Device& d, const bh8_scene* scene, const bh8_came
   if (prm->flags & BH8_FLAG_NO_BATCHING) f.resolve_wait = -1;  // exact tests run at once
   // One instantiation per number of non-central planes with an FP32 side filter; scenes with more
   // planes than filter slots take the generic instantiation (exact test on every gated step).
+  if (f.tracer == BH8_TRACER_LINEAR) {
+    bh8::bh8_linear_kernel<<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out);
+    BH8_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return BH8_OK;
+  }
   switch (f.n_nc <= bh8::kMaxFilterPlanes ? f.n_nc : -1) {
     case 0: bh8::bh8_render_kernel<0><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
     case 1: bh8::bh8_render_kernel<1><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;

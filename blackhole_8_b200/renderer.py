@@ -156,7 +156,7 @@ class Renderer:
         bpp = abi.pixel_bytes(pixel_format)
         scenes = (abi.Scene * n)(*[s.scene for s in snaps])
         cams = (abi.Camera * n)(*[s.camera for s in snaps])
-        prm = abi.Params(nstep or snaps[0].nstep, pixel_format, flags, stripe_rows, 0, 0)
+        prm = snaps[0].params(pixel_format, flags, nstep, stripe_rows)
         res = out if out is not None else {}
         if "pixels" not in res:
             res["pixels"] = np.empty((n, h, w, bpp), np.uint8)
@@ -180,7 +180,7 @@ class Renderer:
     def submit(self, snap, out_array, nstep=None, pixel_format=abi.PIXEL_RGBA8, flags=0):
         """Launch one frame and queue its read-back into out_array (pinned host memory); returns a
         ticket for wait().  Two frames per device may be in flight."""
-        prm = abi.Params(nstep or snap.nstep, pixel_format, flags, 0, 0, 0)
+        prm = snap.params(pixel_format, flags, nstep)
         t = C.c_uint64()
         self._check(self.lib.bh8_submit(self._ctx, C.byref(snap.scene), C.byref(snap.camera), C.byref(prm),
                                         out_array.ctypes.data_as(C.c_void_p), C.byref(t)))
@@ -200,7 +200,7 @@ class Renderer:
 
     def render_device(self, snap, d_pixels, d_cls=None, d_key=None, d_steps=None, nstep=None,
                       pixel_format=abi.PIXEL_RGBA8, flags=0, stripe_rows=0, shard_index=0, shard_count=0):
-        prm = abi.Params(nstep or snap.nstep, pixel_format, flags, stripe_rows, shard_index, shard_count)
+        prm = snap.params(pixel_format, flags, nstep, stripe_rows, shard_index, shard_count)
         self._check(self.lib.bh8_render_device(self._ctx, C.byref(snap.scene), C.byref(snap.camera), C.byref(prm),
                                                C.c_void_p(d_pixels), C.c_void_p(d_cls), C.c_void_p(d_key),
                                                C.c_void_p(d_steps)))

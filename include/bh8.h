@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BH8_ABI_VERSION 1
+#define BH8_ABI_VERSION 2
 #define BH8_MAX_OBJECTS 16
 #define BH8_MAX_TEXTURES 16
 #define BH8_MAX_DEVICES 8
@@ -72,6 +72,14 @@ enum {
   BH8_PIXEL_RGBA8 = 0, /* 4 B/pixel R,G,B,255 */
   BH8_PIXEL_BGRA8 = 1, /* 4 B/pixel B,G,R,255 */
   BH8_PIXEL_BGR8 = 2   /* 3 B/pixel B,G,R: the reference's CV_8UC3 cv::Mat layout */
+};
+
+/* which stepper walks the ray (bh8_params.tracer) */
+enum {
+  BH8_TRACER_GEODESIC = 0, /* Schwarzschild null geodesic, blackhole_solution_test.cc:161-308 */
+  BH8_TRACER_LINEAR = 1    /* flat space: RayTracer::Prograde with BasicLinearRayRecurrence,
+                              ray_tracer.h:17-35,68-85 as driven by ray_tracer_test.cc:140-155;
+                              the scene needs no black hole (bh_index = -1) */
 };
 
 /* bh8_params.flags */
@@ -119,12 +127,15 @@ typedef struct bh8_params {
   int32_t stripe_rows;
   int32_t shard_index;
   int32_t shard_count;
+  int32_t tracer;        /* BH8_TRACER_* */
+  int32_t linear_steps;  /* BH8_TRACER_LINEAR: segments per ray, the 10 of ray_tracer_test.cc:145 */
 } bh8_params;
 
 typedef struct bh8_stats {
   uint64_t rays;         /* rays traced by this call */
   uint64_t steps;        /* geodesic updates executed (reference definition: per-ray count of
-                            u/phi updates up to and including the one whose segment hit) */
+                            u/phi updates up to and including the one whose segment hit); LINEAR:
+                            segments tested */
   uint64_t class_count[4];
   uint64_t tex_oob;      /* texture fetches whose reference index lay outside the image (clamped) */
   double kernel_ms;      /* device time of the render kernel(s), CUDA events, max over devices */

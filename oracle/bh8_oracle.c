@@ -408,19 +408,71 @@ static void trace_pixel(const frame_ctx* f, int x, int y, pixel_result* out, uin
     if (advance(f, &s, -du, out, oob)) return;
 }
 
+static int oracle_render(const bh8_scene* scene, const bh8_camera* cam, int nstep, int linear_steps,
+                         const bh8_oracle_texture* textures, int n_textures, int row0, int row1,
+                         int threads, uint8_t* out_bgr, uint8_t* out_class, int8_t* out_key,
+                         uint16_t* out_steps, bh8_oracle_result* result);
+
+/* One pixel of the flat-space driver, ray_tracer_test.cc:143-145:
+ *   RayTracer(old = camera.focus(), present = camera.PixelVector(x, y, fv))   ray_tracer.h:59-61
+ *   BasicLinearRayRecurrence: vec = present - old; if (vec.vec < 100) vec *= 100.0 / d2   :21-27
+ *   Prograde(manager, dst, steps): FindCollision(old, present) then present + vec          :68-85 */
+static void trace_pixel_linear(const frame_ctx* f, int x, int y, int steps, pixel_result* out, uint64_t* oob) {
+  out->bgr[0] = out->bgr[1] = out->bgr[2] = 0;
+  out->hit = -1;
+  out->steps = 0;
+  vec3 old = f->cam_pos;
+  vec3 present = sub(sub(f->fv, scale(f->vy, (double)(f->width / 2.0 - x))),
+                     scale(f->vz, (double)(f->height / 2.0 - y)));
+  vec3 step = sub(present, old);
+  const double d2 = dot(step, step);
+  if (d2 < 100) step = scale(step, 100.0 / d2);
+  for (int s = 0; s < steps; ++s) {
+    ++out->steps;
+    vec3 inter;
+    const int k = find_collision(f->scene, old, present, &inter);
+    if (k >= 0) {
+      color_of(&f->scene->obj[k], f->textures, f->n_textures, inter, out->bgr, oob);
+      out->hit = k;
+      return;
+    }
+    const vec3 next = add(present, step);
+    old = present;
+    present = next;
+  }
+}
+
 int bh8_oracle_render(const bh8_scene* scene, const bh8_camera* cam, int nstep,
                       const bh8_oracle_texture* textures, int n_textures, int row0, int row1,
                       int threads, uint8_t* out_bgr, uint8_t* out_class, int8_t* out_key,
                       uint16_t* out_steps, bh8_oracle_result* result) {
-  if (!scene || !cam || !out_bgr || scene->n_obj < 1 || scene->n_obj > BH8_MAX_OBJECTS ||
-      scene->bh_index < 0 || scene->bh_index >= scene->n_obj ||
-      scene->obj[scene->bh_index].kind != BH8_KIND_BLACKHOLE || nstep < 2)
-    return -1;
+  return oracle_render(scene, cam, nstep, 0, textures, n_textures, row0, row1, threads, out_bgr, out_class,
+                       out_key, out_steps, result);
+}
+
+int bh8_oracle_render_linear(const bh8_scene* scene, const bh8_camera* cam, int linear_steps,
+                             const bh8_oracle_texture* textures, int n_textures, int row0, int row1,
+                             int threads, uint8_t* out_bgr, uint8_t* out_class, int8_t* out_key,
+                             uint16_t* out_steps, bh8_oracle_result* result) {
+  if (linear_steps < 1) return -1;
+  return oracle_render(scene, cam, 2, linear_steps, textures, n_textures, row0, row1, threads, out_bgr,
+                       out_class, out_key, out_steps, result);
+}
+
+static int oracle_render(const bh8_scene* scene, const bh8_camera* cam, int nstep, int linear_steps,
+                         const bh8_oracle_texture* textures, int n_textures, int row0, int row1,
+                         int threads, uint8_t* out_bgr, uint8_t* out_class, int8_t* out_key,
+                         uint16_t* out_steps, bh8_oracle_result* result) {
+  static const bh8_object no_hole = {BH8_KIND_BLACKHOLE, -1, -1, 0, {{0}}, {0}, {0}, {0}, 0, 0, 1.0, 0};
+  if (!scene || !cam || !out_bgr || scene->n_obj < 1 || scene->n_obj > BH8_MAX_OBJECTS || nstep < 2) return -1;
+  const int has_hole = scene->bh_index >= 0 && scene->bh_index < scene->n_obj &&
+                       scene->obj[scene->bh_index].kind == BH8_KIND_BLACKHOLE;
+  if (!has_hole && !(linear_steps > 0 && scene->bh_index == -1)) return -1;
   frame_ctx f;
   f.scene = scene;
   f.textures = textures;
   f.n_textures = n_textures;
-  f.bh = &scene->obj[scene->bh_index];
+  f.bh = has_hole ? &scene->obj[scene->bh_index] : &no_hole;
   f.cam_pos = v3p(cam->pos);
   f.vx = v3p(cam->vx);
   f.vy = v3p(cam->vy);
@@ -444,7 +496,10 @@ int bh8_oracle_render(const bh8_scene* scene, const bh8_camera* cam, int nstep,
   for (int y = row0; y < row1; ++y) {
     for (int x = 0; x < W; ++x) {
       pixel_result p;
-      trace_pixel(&f, x, y, &p, &oob);
+      if (linear_steps > 0)
+        trace_pixel_linear(&f, x, y, linear_steps, &p, &oob);
+      else
+        trace_pixel(&f, x, y, &p, &oob);
       const size_t i = (size_t)y * W + x; /* :214 */
       out_bgr[i * 3 + 0] = p.bgr[0];
       out_bgr[i * 3 + 1] = p.bgr[1];

@@ -37,6 +37,13 @@ int bh8_oracle_render(const bh8_scene* scene, const bh8_camera* cam, int nstep,
                       int threads, uint8_t* out_bgr, uint8_t* out_class, int8_t* out_key,
                       uint16_t* out_steps, bh8_oracle_result* result);
 
+/* Flat-space tracer (ray_tracer_test.cc:140-155, ray_tracer.h:17-35,68-85): up to linear_steps
+ * segments per ray; the scene needs no black hole (bh_index = -1). */
+int bh8_oracle_render_linear(const bh8_scene* scene, const bh8_camera* cam, int linear_steps,
+                             const bh8_oracle_texture* textures, int n_textures, int row0, int row1,
+                             int threads, uint8_t* out_bgr, uint8_t* out_class, int8_t* out_key,
+                             uint16_t* out_steps, bh8_oracle_result* result);
+
 /* Single-function known-answer hooks (tests/test_oracle.py). */
 double bh8_oracle_G(double mass, double u, double b);
 double bh8_oracle_solve_g(double mass, double b);

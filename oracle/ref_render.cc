@@ -28,6 +28,7 @@
 #include <omp.h>
 #endif
 
+#include "blackhole/ray_tracer.h"
 #include "scenes.h"
 
 namespace {
@@ -133,6 +134,33 @@ PixelResult TracePixel(const blackhole::Camera<value_type>& camera, const vector
   return out;
 }
 
+// One pixel of the flat-space driver, ray_tracer_test.cc:143-145: the reference's RayTracer class
+// itself (BasicLinearRayRecurrence, Prograde) does the work.  Prograde writes the colour but does
+// not say which object was hit or after how many segments, so the same march is repeated with
+// FindCollision to recover the key and the count (identical arithmetic, ray_tracer.h:24-31,68-85).
+template <typename Manager>
+PixelResult TracePixelLinear(const blackhole::Camera<value_type>& camera, const vector_type& fv,
+                             const Manager& manager, int x, int y, int steps) {
+  PixelResult out;
+  blackhole::RayTracer ray_tracer(camera.focus(), camera.PixelVector(x, y, fv));
+  Manager& mutable_manager = const_cast<Manager&>(manager);
+  ray_tracer.Prograde(mutable_manager, out.bgr, steps);
+
+  point_type old = camera.focus(), present = camera.PixelVector(x, y, fv), inter;
+  blackhole::BasicLinearRayRecurrence<point_type> next(old, present);
+  for (int s = 0; s < steps; ++s) {
+    ++out.steps;
+    if (const auto* obj = manager.FindCollision(old, present, &inter); obj != nullptr) {
+      out.hit = obj;
+      break;
+    }
+    auto p = next(old, present);
+    old = present;
+    present = p;
+  }
+  return out;
+}
+
 void PrintVec(FILE* f, const char* name, const double* v, int n, bool comma = true) {
   std::fprintf(f, "\"%s\": [", name);
   for (int i = 0; i < n; ++i) std::fprintf(f, "%s%.17g", i ? ", " : "", v[i]);
@@ -185,9 +213,9 @@ int main(int argc, char** argv) {
     return 2;
   }
   if (nstep <= 0) nstep = scene->nstep;
+  const int linear_steps = scene->linear_steps;
   auto& manager = bh8scenes::manager_type::GetInstance();
   const auto& camera = scene->camera;
-  const auto& blackhole = *scene->blackhole;
 
   const size_t npix = static_cast<size_t>(width) * height;
   std::vector<unsigned char> bgr(npix * 3, 0), cls(npix, 0);
@@ -208,7 +236,9 @@ int main(int argc, char** argv) {
 #pragma omp parallel for schedule(dynamic, 4)
       for (int y = row0; y < row1; ++y) {
         for (int x = 0; x < width; ++x) {
-          const PixelResult p = TracePixel(camera, fv, blackhole, manager, x, y, nstep);
+          const PixelResult p = linear_steps > 0
+                                    ? TracePixelLinear(camera, fv, manager, x, y, linear_steps)
+                                    : TracePixel(camera, fv, *scene->blackhole, manager, x, y, nstep);
           const size_t i = static_cast<size_t>(y) * width + x;  // :214
           bgr[i * 3 + 0] = p.bgr[0];
           bgr[i * 3 + 1] = p.bgr[1];
@@ -251,8 +281,8 @@ int main(int argc, char** argv) {
     std::fprintf(stderr, "cannot write %s\n", json_path.c_str());
     return 2;
   }
-  std::fprintf(jf, "{\"cfg\": %d, \"frame\": %d, \"nstep\": %d, \"width\": %d, \"height\": %d,\n", cfg, frame,
-               nstep, width, height);
+  std::fprintf(jf, "{\"cfg\": %d, \"frame\": %d, \"nstep\": %d, \"linear_steps\": %d, \"width\": %d, \"height\": %d,\n",
+               cfg, frame, nstep, linear_steps, width, height);
   std::fprintf(jf, " \"camera\": {");
   PrintVec(jf, "pos", cam.pos, 3);
   PrintVec(jf, "vx", cam.vx, 3);

@@ -18,6 +18,8 @@
 //          6 hole moved off the disc's plane (arrow keys, blackhole_solution_test.cc:391-396) and
 //            camera tilted; 7 camera turned away from the hole (mirrored-start rays, the atan quirk);
 //          8 more planes than the kernel has filter slots; 9 camera inside the photon sphere
+//   cfg 10 the flat-space scene of ray_tracer_test.cc:45-98 (800x450, 3 textured rectangles + chess
+//          floor, no hole), frame k after k rounds of its object animation (:237-261)
 //
 // Because ObjectManager is a leaked singleton without enumeration (object_manager.h:30-33,92) the
 // builder keeps its own list of what it inserted, in insertion order.
@@ -58,6 +60,8 @@ struct Scene {
   blackhole::StaticBlackhole<value_type>* blackhole = nullptr;
   blackhole::Annulus<value_type>* disc = nullptr;
   int nstep = 20;
+  int linear_steps = 0;  // > 0: flat-space scene, traced with RayTracer::Prograde(.., linear_steps)
+  object_type* movers[3] = {nullptr, nullptr, nullptr};  // cfg 10: mooni, karina, winter
 
   Scene(int w, int h, value_type fov) : camera(w, h, fov) {}
 };
@@ -83,9 +87,9 @@ inline void AddDisc(Scene* s, manager_type& m, const std::string& texdir) {
   s->disc = id.second;
 }
 
-inline void AddRectangle(Scene* s, manager_type& m, const std::string& texdir, const std::string& tex,
-                         double x1, double y1, double z1, double x2, double y2, double z2, double x3,
-                         double y3, double z3, double x4, double y4, double z4) {
+inline object_type* AddRectangle(Scene* s, manager_type& m, const std::string& texdir, const std::string& tex,
+                                 double x1, double y1, double z1, double x2, double y2, double z2, double x3,
+                                 double y3, double z3, double x4, double y4, double z4) {
   auto id = m.InsertObject<blackhole::Rectangle>(x1, y1, z1, x2, y2, z2, x3, y3, z3, x4, y4, z4);
   id.second->SetTexture(LoadTexture(texdir, tex));
   Inserted e;
@@ -94,6 +98,7 @@ inline void AddRectangle(Scene* s, manager_type& m, const std::string& texdir, c
   e.object = id.second;
   e.texture = tex;
   s->objects.push_back(e);
+  return id.second;
 }
 
 inline void AddBackground(Scene* s, manager_type& m, const std::string& texdir) {
@@ -201,6 +206,42 @@ inline Scene* Build(int cfg, int width, int height, int frame, const std::string
       AddBackground(s, m, texdir);
       AddBlackhole(s, m, 10);
       break;
+    case 10: {  // ray_tracer_test.cc:45-98
+      s = new Scene(width, height, blackhole::pi / 2);
+      s->camera.MoveTo(-400, 120, 100);
+      s->camera.RotateY(-blackhole::pi / 24);
+      s->camera.RotateZ(blackhole::pi / 12);
+      s->movers[0] = AddRectangle(s, m, texdir, "mooni.jpeg", 100, 120, 100, 100, 0, 100, 100, 0, 0, 100, 120, 0);
+      s->movers[1] = AddRectangle(s, m, texdir, "karina.jpeg", 100, 0, 150, 100, -100, 150, 100, -100, 0, 100, 0, 0);
+      s->movers[2] = AddRectangle(s, m, texdir, "winter.jpg", -100, 50, 100, -100, -50, 100, -100, -50, 0, -100, 50, 0);
+      AddChess(s, m, 10);
+      s->linear_steps = 10;  // Prograde(manager, dst, 10), ray_tracer_test.cc:145
+      int karina_move_direction = 1;
+      for (int k = 0; k < frame; ++k) {  // "Movement test", ray_tracer_test.cc:237-261
+        s->movers[1]->MoveX(3 * karina_move_direction);
+        if (auto x = s->movers[1]->position()[0]; x > 100)
+          karina_move_direction = -1;
+        else if (x < 0)
+          karina_move_direction = 1;
+        {
+          const auto y = -120.0, z = -100.0;
+          s->movers[0]->MoveY(-y / 2);
+          s->movers[0]->MoveZ(-z / 2);
+          s->movers[0]->RotateX(blackhole::pi / 180);
+          s->movers[0]->MoveY(y / 2);
+          s->movers[0]->MoveZ(z / 2);
+        }
+        {
+          const auto x = 100.0, z = -100.0;
+          s->movers[2]->MoveX(-x);
+          s->movers[2]->MoveZ(-z / 2);
+          s->movers[2]->RotateY(blackhole::pi / 120);
+          s->movers[2]->MoveX(x);
+          s->movers[2]->MoveZ(z / 2);
+        }
+      }
+      break;
+    }
     default:
       return nullptr;
   }

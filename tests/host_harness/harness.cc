@@ -75,6 +75,25 @@ extern "C" int bh8_harness_render(const bh8_scene* scene, const bh8_camera* cam,
   if (rc != BH8_OK) return rc;
   const HostFetch fetch{textures};
   counters[0] = counters[1] = 0;
+  if (f.tracer == BH8_TRACER_LINEAR) {
+    for (int y = 0; y < f.height; ++y)
+      for (int x = 0; x < f.width; ++x) {
+        int hit = -1;
+        double hp[3] = {0, 0, 0};
+        const int steps = bh8::trace_linear(f, x, y, &hit, hp);
+        uint32_t bgr = 0, oob = 0;
+        if (hit >= 0) bgr = bh8::shade(f, hit, hp, fetch, &oob);
+        const size_t i = static_cast<size_t>(y) * f.width + x;
+        out_bgr[3 * i] = bgr & 255;
+        out_bgr[3 * i + 1] = (bgr >> 8) & 255;
+        out_bgr[3 * i + 2] = (bgr >> 16) & 255;
+        out_class[i] = (uint8_t)(hit >= 0 ? f.obj[hit].cls : BH8_CLASS_BACKGROUND);
+        out_key[i] = (int8_t)(hit >= 0 ? f.obj[hit].key : -1);
+        out_steps[i] = (uint16_t)steps;
+        counters[0] += steps;
+      }
+    return BH8_OK;
+  }
   switch ((filter_slots >= 0 && f.n_nc <= 4) ? f.n_nc : -1) {
     case 0: trace_frame<0>(f, fetch, out_bgr, out_class, out_key, out_steps, counters); break;
     case 1: trace_frame<1>(f, fetch, out_bgr, out_class, out_key, out_steps, counters); break;

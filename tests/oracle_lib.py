@@ -41,6 +41,7 @@ def lib():
         _LIB.bh8_oracle_solve_g.restype = C.c_double
         _LIB.bh8_oracle_solve_g.argtypes = [C.c_double] * 2
         _LIB.bh8_oracle_render.restype = C.c_int
+        _LIB.bh8_oracle_render_linear.restype = C.c_int
     return _LIB
 
 
@@ -72,7 +73,11 @@ def render(snap, nstep=None, threads=None, rows=None):
     steps = np.zeros((h, w), np.uint16)
     res = OracleResult()
     r0, r1 = rows if rows else (0, h)
-    rc = L.bh8_oracle_render(C.byref(snap.scene), C.byref(snap.camera), C.c_int(nstep or snap.nstep),
+    if snap.linear_steps > 0:
+        fn, count = L.bh8_oracle_render_linear, snap.linear_steps
+    else:
+        fn, count = L.bh8_oracle_render, nstep or snap.nstep
+    rc = fn(C.byref(snap.scene), C.byref(snap.camera), C.c_int(count),
                              tarr, C.c_int(len(texs)), C.c_int(r0), C.c_int(r1),
                              C.c_int(threads or os.cpu_count() or 1),
                              bgr.ctypes.data_as(C.c_void_p), cls.ctypes.data_as(C.c_void_p),

@@ -44,7 +44,7 @@ def harness_render(snap, nstep=None, filter_slots=4):
     tarr = (HarnessTexture * max(1, len(texs)))()
     for i, t in enumerate(texs):
         tarr[i] = HarnessTexture(t.ctypes.data, t.shape[0], t.shape[1])
-    prm = abi.Params(nstep or snap.nstep, abi.PIXEL_BGR8, 0, 0, 0, 0)
+    prm = snap.params(abi.PIXEL_BGR8, 0, nstep)
     out = {"bgr": np.zeros((h, w, 3), np.uint8), "cls": np.zeros((h, w), np.uint8),
            "key": np.zeros((h, w), np.int8), "steps": np.zeros((h, w), np.uint16)}
     err = C.create_string_buffer(256)

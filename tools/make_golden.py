@@ -42,6 +42,9 @@ SMALL = {
     "cfg9_inside_320x180": (9, 320, 180, 0, None),
     "cfg1_nstep2_320x180": (1, 320, 180, 0, 2),
     "cfg1_tiny_5x3": (1, 5, 3, 0, None),
+    # flat space: the ray_tracer_test.cc scene; frame 0 == the UNCHANGED ray_tracer_test's frame
+    "cfg10_flat_800x450": (10, 800, 450, 0, None),
+    "cfg10_flat_frame25_640x360": (10, 640, 360, 25, None),
 }
 DIGEST_ONLY = {
     "cfg1_1920x1080": (1, 1920, 1080, 0, None),
