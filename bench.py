@@ -219,7 +219,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batching", action="store_true")
-    ap.add_argument("--workload", default="cfg1_spin", choices=["cfg1_spin", "cfg3_flythrough", "cfg1_static"],
+    ap.add_argument("--workload", default="cfg1_spin",
+                    choices=["cfg1_spin", "cfg3_flythrough", "cfg1_static", "cfg10_flat"],
                     help="frame sequence: configs[1] with the disc spinning frame to frame as in the "
                          "reference's loop (default), the configs[3] fly-through, or configs[1] frame 0 only")
     args = ap.parse_args()
@@ -258,6 +259,10 @@ def main():
     # N, no data-path collective.
     from blackhole_8_b200 import sharding
     if args.workload == "cfg1_static":
+        seq = [base]
+    elif args.workload == "cfg10_flat":  # the ray_tracer_test.cc scene (linear tracer) at 1080p
+        base = load_snapshot("cfg10_flat_800x450").with_resolution(W, H)
+        r.set_textures(base, load_texture)
         seq = [base]
     else:
         seq = frame_sequence(args.workload, 240)

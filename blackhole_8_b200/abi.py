@@ -167,4 +167,6 @@ class SceneSnapshot:
         d["camera"]["focus_len"] = float(width / (2.0 * np.tan(fov / 2.0)))
         d["camera"]["width"] = d["width"] = int(width)
         d["camera"]["height"] = d["height"] = int(height)
-        return SceneSnapshot.from_dict(d)
+        out = SceneSnapshot.from_dict(d)
+        out.meta = dict(self.meta)
+        return out
