@@ -57,82 +57,89 @@ struct DeviceFetch {
   }
 };
 
-// Register budget.  The stepping loop needs ~50 registers, the exact segment test ~110.  Letting the
+// Register budget.  The stepping loop needs ~45 registers, the exact segment test ~110.  Letting the
 // second set the kernel's register count would halve the occupancy that hides the FP64 pipe's
-// latency, so a lane that enters the exact test first parks its state in a per-thread mailbox in
-// shared memory and re-loads it afterwards: no stepping value is live inside the test, and the test
-// is entered about once per ray.  (volatile: the compiler must not forward the stores to the loads,
+// latency, so a lane that enters the exact test first parks its state in its mailbox (shared
+// memory) and re-loads it afterwards: no stepping value is live inside the test, and the test is
+// entered about once per ray.  (volatile: the compiler must not forward the stores to the loads,
 // which would keep the values alive in registers.)
-// Mailbox, stride kThreads.  doubles: [0..2] e2 (hit point once the ray has ended), [3] u, [4] phi,
-// [5] dphi_prev, [6] delta, [7] phi_trig, [8] t, [9] du_h, [10] binv2.  ints: [0] i, [1] next_evt,
-// [2] state, [3] fbits, [4] fstep, [5] steps, [6] hit_obj, [7] flags, [8] gate_in, [9] gate_out,
-// [10] lo, [11] span, [12..] fa/fb bit patterns.  du_h, binv2, flags, gates, lo, fa/fb never change
-// after setup: written once.
-constexpr int kMailDoubles = 11;
-constexpr int kMailInts = 12 + 2 * kMaxFilterPlanes;
+// Mailbox, stride kThreads.  doubles: bh8::Mail's slots [0..6] (e2 / hit point, and the frozen lane's
+// delta, t, phi_trig, du_h), then [7] u, [8] phi, [9] dphi_prev, [10] binv2.  ints: Mail's [0] span,
+// then [1] i, [2] next_evt, [3] state, [4] fbits, [5] fstep, [6] steps, [7] hit_obj, [8] flags,
+// [9] gate_in, [10] gate_out, [11] lo, [12..] fa/fb bit patterns.  binv2, flags, gates, lo, fa/fb
+// never change after setup: written once.
+constexpr int kMailDoubles = kMailDoublesRay + 4;
+constexpr int kMailInts = kMailIntsRay + 11 + 2 * kMaxFilterPlanes;
+enum : int { kKdU = kMailDoublesRay, kKdPhi, kKdDphi, kKdBinv2 };
+enum : int { kKwI = kMailIntsRay, kKwNext, kKwState, kKwFbits, kKwFstep, kKwSteps, kKwHit, kKwFlags, kKwGateIn,
+             kKwGateOut, kKwLo, kKwFab };
 
 template <int NN>
 __device__ __forceinline__ void lane_park_constants(const Lane<NN>& L, volatile double* md, volatile int* mi) {
-  md[9 * kThreads] = L.du_h;
-  md[10 * kThreads] = L.binv2;
-  mi[7 * kThreads] = L.flags;
-  mi[8 * kThreads] = L.gate_in;
-  mi[9 * kThreads] = L.gate_out;
-  mi[10 * kThreads] = L.lo;
+  md[kKdBinv2 * kThreads] = L.binv2;
+  mi[kKwFlags * kThreads] = L.flags;
+  mi[kKwGateIn * kThreads] = L.gate_in;
+  mi[kKwGateOut * kThreads] = L.gate_out;
+  mi[kKwLo * kThreads] = L.lo;
 #pragma unroll
   for (int j = 0; j < (NN > 0 ? NN : 0); ++j) {
-    mi[(12 + 2 * j) * kThreads] = __float_as_int(L.fa[j]);
-    mi[(13 + 2 * j) * kThreads] = __float_as_int(L.fb[j]);
+    mi[(kKwFab + 2 * j) * kThreads] = __float_as_int(L.fa[j]);
+    mi[(kKwFab + 2 * j + 1) * kThreads] = __float_as_int(L.fb[j]);
   }
 }
 
+// What a frozen lane still carries in registers and the exact test needs or changes.
 template <int NN>
 __device__ __forceinline__ void lane_park(const Lane<NN>& L, volatile double* md, volatile int* mi) {
-  md[3 * kThreads] = L.u;
-  md[4 * kThreads] = L.phi;
-  md[5 * kThreads] = L.dphi_prev;
-  md[6 * kThreads] = L.delta;
-  md[7 * kThreads] = L.phi_trig;
-  md[8 * kThreads] = L.t;
-  mi[0 * kThreads] = L.i;
-  mi[1 * kThreads] = L.next_evt;
-  mi[2 * kThreads] = L.state;
-  mi[3 * kThreads] = (int)L.fbits;
-  mi[4 * kThreads] = L.fstep;
-  mi[5 * kThreads] = L.steps;
-  mi[6 * kThreads] = L.hit_obj;
-  mi[11 * kThreads] = (int)L.span;
+  md[kKdU * kThreads] = L.u;
+  md[kKdPhi * kThreads] = L.phi;
+  md[kKdDphi * kThreads] = L.dphi_prev;
+  mi[kKwI * kThreads] = L.i;
+  mi[kKwNext * kThreads] = L.next_evt;
+  mi[kKwState * kThreads] = L.state;
+  mi[kKwFbits * kThreads] = (int)L.fbits;
+  mi[kKwFstep * kThreads] = L.fstep;
+  mi[kKwSteps * kThreads] = L.steps;
+  mi[kKwHit * kThreads] = L.hit_obj;
 }
 
+// Re-load a lane from its mailbox: frozen (as lane_freeze leaves it) or, if the exact test cleared
+// the segment (state kRun), travelling again with the values the test left in Mail's slots.
 template <int NN>
-__device__ __forceinline__ void lane_unpark(Lane<NN>& L, const volatile double* md, const volatile int* mi) {
-  L.u = md[3 * kThreads];
-  L.phi = md[4 * kThreads];
-  L.dphi_prev = md[5 * kThreads];
-  L.delta = md[6 * kThreads];
-  L.phi_trig = md[7 * kThreads];
-  L.t = md[8 * kThreads];
-  L.du_h = md[9 * kThreads];
-  L.binv2 = md[10 * kThreads];
-  L.i = mi[0 * kThreads];
-  L.next_evt = mi[1 * kThreads];
-  L.state = mi[2 * kThreads];
-  L.fbits = (uint32_t)mi[3 * kThreads];
-  L.fstep = mi[4 * kThreads];
-  L.steps = mi[5 * kThreads];
-  L.hit_obj = mi[6 * kThreads];
-  L.flags = mi[7 * kThreads];
-  L.gate_in = mi[8 * kThreads];
-  L.gate_out = mi[9 * kThreads];
-  L.lo = mi[10 * kThreads];
-  L.span = (uint32_t)mi[11 * kThreads];
+__device__ __forceinline__ void lane_unpark(Lane<NN>& L, const Mail m, const volatile double* md,
+                                            const volatile int* mi) {
+  L.u = md[kKdU * kThreads];
+  L.phi = md[kKdPhi * kThreads];
+  L.dphi_prev = md[kKdDphi * kThreads];
+  L.binv2 = md[kKdBinv2 * kThreads];
+  L.i = mi[kKwI * kThreads];
+  L.next_evt = mi[kKwNext * kThreads];
+  L.state = mi[kKwState * kThreads];
+  L.fbits = (uint32_t)mi[kKwFbits * kThreads];
+  L.fstep = mi[kKwFstep * kThreads];
+  L.steps = mi[kKwSteps * kThreads];
+  L.hit_obj = mi[kKwHit * kThreads];
+  L.flags = mi[kKwFlags * kThreads];
+  L.gate_in = mi[kKwGateIn * kThreads];
+  L.gate_out = mi[kKwGateOut * kThreads];
+  L.lo = mi[kKwLo * kThreads];
 #pragma unroll
   for (int j = 0; j < (NN > 0 ? NN : 0); ++j) {
-    L.fa[j] = __int_as_float(mi[(12 + 2 * j) * kThreads]);
-    L.fb[j] = __int_as_float(mi[(13 + 2 * j) * kThreads]);
+    L.fa[j] = __int_as_float(mi[(kKwFab + 2 * j) * kThreads]);
+    L.fb[j] = __int_as_float(mi[(kKwFab + 2 * j + 1) * kThreads]);
   }
   L.bgr = 0;
   L.oob = 0;
+  L.t = 0.0;
+  if (L.state == kRun) {
+    lane_thaw(L, m);
+  } else {
+    L.delta = 0.0;
+    L.du_h = 0.0;
+    L.phi_trig = INFINITY;
+    L.span = 0xffffffffu;
+    L.inc = 0;
+  }
 }
 
 // Pixel store + optional maps + optional counters, shared by both kernels.  RGBA8 / BGRA8 go through
@@ -227,23 +234,24 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
   __shared__ int sh_mi[kMailInts * kThreads];
   double* const md = sh_md + tid;
   int* const mi = sh_mi + tid;
-  const E2Ref e2r{md, kThreads};
+  const Mail mail{md, mi, kThreads};
   Lane<NN> L;
-  L.state = kDead;
+  lane_inert(L);
+  L.flags = 0;
   L.hit_obj = -1;
   L.steps = 0;
   L.bgr = 0;
   L.oob = 0;
   if (inside) {
-    lane_setup(f, x, y, L, e2r);
+    lane_setup(f, x, y, L, mail);
     lane_park_constants(L, md, mi);
   }
   int waited = 0;
   for (;;) {
-    // lean stepping: a few updates per pair of warp votes
+    // Lean stepping: the same straight-line update for every lane (frozen lanes are inert, see
+    // lane_freeze), a few updates per round of warp votes.
 #pragma unroll
-    for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k)
-      if (L.state == kRun) lane_update(f, L);
+    for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k) lane_update(f, L, mail);
     const unsigned runs = __ballot_sync(0xffffffffu, L.state == kRun);
     const unsigned pend = __ballot_sync(0xffffffffu, (unsigned)(L.state - kPend) < 2u);
     if (pend == 0u) {
@@ -258,12 +266,13 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
       lane_park(L, md, mi);
       {
         Lane<NN> T;  // the test works on its own copy, loaded from the mailbox
-        lane_unpark(T, md, mi);
-        lane_exact(f, T, e2r);
-        if (T.state == kPendChord) lane_exact(f, T, e2r);  // event right after a cleared segment
+        lane_unpark(T, mail, md, mi);
+        lane_exact(f, T, mail);
+        if (T.state == kPendChord) lane_exact(f, T, mail);  // event right after a cleared segment
+        if (T.state == kRun) lane_freeze(T, mail, kRun);    // hand the thawed values over through Mail
         lane_park(T, md, mi);
       }
-      lane_unpark(L, md, mi);
+      lane_unpark(L, mail, md, mi);
     }
   }
   const int steps = L.steps;
@@ -271,7 +280,7 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
   // ---- colour ------------------------------------------------------------------------------------
   if (!inside) L.hit_obj = -1;
   L.oob = 0;
-  lane_shade(f, L, e2r, DeviceFetch{tex});
+  lane_shade(f, L, mail, DeviceFetch{tex});
   const uint32_t bgr = L.bgr, oob = L.oob;
   int cls = BH8_CLASS_BACKGROUND, key = -1;
   if (inside && L.hit_obj >= 0) {

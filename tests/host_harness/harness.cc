@@ -23,25 +23,33 @@ struct HostFetch {
   }
 };
 
+static int g_frozen_updates = 0;
+extern "C" void bh8_harness_set_frozen_updates(int n) { g_frozen_updates = n; }
+
 template <int NN>
 static void trace_frame(const Bh8Frame& f, const HostFetch& fetch, uint8_t* out_bgr, uint8_t* out_class,
                         int8_t* out_key, uint16_t* out_steps, uint64_t* counters) {
   for (int y = 0; y < f.height; ++y) {
     for (int x = 0; x < f.width; ++x) {
       bh8::Lane<NN> L;
-      double e2[3];
-      const bh8::E2Ref e2r{e2, 1};
-      bh8::lane_setup(f, x, y, L, e2r);
+      double md[bh8::kMailDoublesRay];
+      int32_t mw[bh8::kMailIntsRay];
+      const bh8::Mail mail{md, mw, 1};
+      bh8::lane_setup(f, x, y, L, mail);
       while (L.state != bh8::kDead) {  // the kernel's per-lane sequence, one lane, no batching
         if (L.state == bh8::kRun) {
           counters[0]++;
-          bh8::lane_update(f, L);
+          bh8::lane_update(f, L, mail);
         } else {
+          // In the kernel a frozen lane keeps executing the warp's straight-line updates until the
+          // warp attends to it: they must not change anything.
+          for (int k = 0; k < g_frozen_updates; ++k) bh8::lane_update(f, L, mail);
           counters[1]++;
-          bh8::lane_exact(f, L, e2r);
+          bh8::lane_exact(f, L, mail);
         }
       }
-      bh8::lane_shade(f, L, e2r, fetch);
+      for (int k = 0; k < g_frozen_updates; ++k) bh8::lane_update(f, L, mail);  // ended rays too
+      bh8::lane_shade(f, L, mail, fetch);
       const uint32_t bgr = L.bgr;
       int cls = BH8_CLASS_BACKGROUND, key = -1;
       if (L.hit_obj >= 0) {

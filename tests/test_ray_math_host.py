@@ -116,3 +116,20 @@ def test_sincos_primitive_is_within_one_ulp():
                          c.ctypes.data_as(C.c_void_p))
     assert np.abs(s - np.sin(x)).max() <= 2.3e-16
     assert np.abs(c - np.cos(x)).max() <= 2.3e-16
+
+
+@pytest.mark.parametrize("name", ["cfg1_640x360", "cfg2_640x360", "cfg9_inside_320x180", "cfg6_offplane_400x225"])
+def test_frozen_lanes_are_inert(name):
+    """The kernel's warps run the straight-line update for every lane, frozen (parked / ended) ones
+    included.  Emulate that: apply 5 extra updates to each frozen lane before its exact test and after
+    its end -- the frame must not change in any byte."""
+    g = O.load_golden(name)
+    L = harness()
+    a = harness_render(g["snap"])
+    L.bh8_harness_set_frozen_updates(5)
+    try:
+        b = harness_render(g["snap"])
+    finally:
+        L.bh8_harness_set_frozen_updates(0)
+    for k in ("bgr", "cls", "key", "steps"):
+        assert np.array_equal(a[k], b[k]), k
