@@ -133,7 +133,11 @@ def ncu_summary():
             "smsp__sass_average_branch_targets_threads_uniform.pct": "uniform_branch_targets_pct",
             "launch__registers_per_thread": "registers_per_thread",
             "sm__warps_active.avg.per_cycle_active": "warps_per_sm",
-            "gpu__time_duration.sum": "kernel_us_under_ncu"}
+            "gpu__time_duration.sum": "kernel_us_under_ncu",
+            "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed": "dfma_per_cycle",
+            "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed": "dmul_per_cycle",
+            "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed": "dadd_per_cycle",
+            "sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained": "fp64_lanes_per_cycle_peak"}
     out = {"source": os.path.relpath(files[-1], ROOT)}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     dram = 0.0
@@ -146,6 +150,9 @@ def ncu_summary():
         if m.group(1) in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             dram += float(m.group(3)) * scale.get(m.group(2), 1.0)
     out["dram_bytes_per_launch"] = dram
+    if "dfma_per_cycle" in out and out.get("fp64_lanes_per_cycle_peak"):
+        flops = 2 * out.pop("dfma_per_cycle") + out.pop("dmul_per_cycle", 0.0) + out.pop("dadd_per_cycle", 0.0)
+        out["executed_fp64_flop_frac_of_peak"] = flops / (2 * out.pop("fp64_lanes_per_cycle_peak"))
     return out
 
 
