@@ -405,6 +405,12 @@ def main():
                 "convention": "SURVEY 8(d) W_sm100: %d flops/geodesic step, 385/ray setup, 130/terminal hit"
                               % (FLOPS_PER_STEP_BASE + FLOPS_PER_EXTRA_OBJECT * n_extra)}
 
+    # precision study: the bare update chain in FP64 (as shipped) and FP32, same launch shape
+    step64, step32 = r.measure_stepping(False), r.measure_stepping(True)
+    roofline["precision_study"] = {
+        "fp64_updates_per_s": step64, "fp32_updates_per_s": step32, "fp32_over_fp64": step32 / step64,
+        "renderer_updates_per_s": st.steps / world / (ms_per_step * 1e-3),
+        "note": "bare geodesic update chain, no hit logic; FP32 parity cost measured in tests/test_precision_study.py"}
     ncu = ncu_summary()
     if ncu:
         roofline["traffic"] = ncu.pop("dram_bytes_per_launch", None)  # bytes/launch from the ncu capture

@@ -26,7 +26,10 @@
 namespace bh8 {
 
 constexpr int kTileW = 32;
-constexpr int kTileH = 8;
+#ifndef BH8_TILE_H
+#define BH8_TILE_H 8  // tile rows per CTA (multiple of 4: a warp is an 8x4 patch)
+#endif
+constexpr int kTileH = BH8_TILE_H;
 constexpr int kThreads = kTileW * kTileH;
 constexpr int kMaxFilterPlanes = 4;
 #ifndef BH8_UPDATES_PER_VOTE
@@ -326,6 +329,37 @@ bh8_linear_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
     key = f.obj[hit].key;
   }
   store_pixel(f, out, sh_rgba, sh_red, tid, lane, slot, x0, y0, x, y, inside, bgr, oob, cls, key, steps);
+}
+
+// Precision study: the bare geodesic update chain (u += du; G; rsqrt; trapezoid; two compares) for
+// `updates` steps per thread, in FP64 exactly as lane_update runs it, or in FP32 (FFMA + MUFU.RSQ).
+// Nothing else of the renderer is in here: it isolates what the choice of precision can buy for
+// the stepping loop.  Each thread gets its own impact parameter so the compiler
+// cannot share work; the result is folded into a checksum the host ignores.
+template <typename Real>
+__global__ void __launch_bounds__(256, 5)
+bh8_stepping_probe_kernel(double* sink, int updates, double two_m, double u0, double du, double binv2_0) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  Real u = (Real)u0, phi = 0, dphi_prev = 0;
+  const Real delta = (Real)(du * (1.0 + 1e-4 * (gid & 1023))), du_h = (Real)0.5 * delta;
+  const Real binv2 = (Real)(binv2_0 * (1.0 + 1e-3 * (gid & 255))), tm = (Real)two_m;
+  const Real trig = (Real)1e30;
+  int parked = 0;
+  for (int i = 0; i < updates; ++i) {
+    u += delta;
+    const Real g = fma(u * u, fma(tm, u, (Real)-1), binv2);
+    Real dphi;
+    if (sizeof(Real) == 8) {
+      dphi = (Real)fast_rsqrt((double)g);
+    } else {
+      dphi = (Real)rsqrtf((float)g);
+    }
+    const Real t = (dphi_prev + dphi) * du_h;
+    dphi_prev = dphi;
+    phi += t;
+    if (!(t <= (Real)1) || !(phi < trig)) ++parked;
+  }
+  if (phi == (Real)123.456 || parked == updates + 1) sink[0] = (double)phi + parked;
 }
 
 // FP64 pipe peak: 8 independent DFMA chains per thread, enough warps to fill every SM.

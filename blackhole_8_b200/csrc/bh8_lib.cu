@@ -614,6 +614,42 @@ int bh8_host_alloc(void** p, size_t bytes) {
 
 int bh8_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? BH8_OK : BH8_ECUDA; }
 
+int bh8_measure_stepping(bh8_ctx* ctx, int fp32, double* updates_per_s) {
+  if (!ctx || !updates_per_s) return BH8_EINVAL;
+  Device& d = ctx->dev[0];
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  cudaDeviceProp prop;
+  BH8_CUDA(ctx, cudaGetDeviceProperties(&prop, d.ordinal));
+  double* sink = nullptr;
+  BH8_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&sink), sizeof(double)));
+  const int blocks = prop.multiProcessorCount * 5 * 8, threads = 256, updates = 390;
+  cudaEvent_t e0, e1;
+  BH8_CUDA(ctx, cudaEventCreate(&e0));
+  BH8_CUDA(ctx, cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    BH8_CUDA(ctx, cudaEventRecord(e0, d.stream));
+    // M = 10, camera at r0 = 2040, b = 300: G stays positive over 390 steps of du = 4e-6
+    if (fp32)
+      bh8::bh8_stepping_probe_kernel<float><<<blocks, threads, 0, d.stream>>>(sink, updates, 20.0, 4.9e-4, 4e-6, 1.1e-5);
+    else
+      bh8::bh8_stepping_probe_kernel<double><<<blocks, threads, 0, d.stream>>>(sink, updates, 20.0, 4.9e-4, 4e-6, 1.1e-5);
+    BH8_CUDA(ctx, cudaGetLastError());
+    BH8_CUDA(ctx, cudaEventRecord(e1, d.stream));
+    BH8_CUDA(ctx, cudaEventSynchronize(e1));
+    ctx->launches++;
+    float ms = 0;
+    BH8_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    const double rate = static_cast<double>(blocks) * threads * updates / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *updates_per_s = best;
+  return BH8_OK;
+}
+
 int bh8_measure_fp64_peak(bh8_ctx* ctx, double* flops_per_s, double* seconds_run) {
   if (!ctx || !flops_per_s) return BH8_EINVAL;
   Device& d = ctx->dev[0];

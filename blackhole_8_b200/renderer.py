@@ -63,6 +63,7 @@ def load_library(path=None):
         "bh8_host_alloc": (i32, [C.POINTER(vp), C.c_size_t]),
         "bh8_host_free": (i32, [vp]),
         "bh8_measure_fp64_peak": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "bh8_measure_stepping": (i32, [vp, i32, C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -244,6 +245,11 @@ class Renderer:
 
     def pinned(self, shape, dtype=np.uint8):
         return PinnedBuffer(self.lib, shape, dtype)
+
+    def measure_stepping(self, fp32):
+        v = C.c_double()
+        self._check(self.lib.bh8_measure_stepping(self._ctx, 1 if fp32 else 0, C.byref(v)))
+        return v.value
 
     def measure_fp64_peak(self):
         f, s = C.c_double(), C.c_double()

@@ -210,6 +210,10 @@ int bh8_memset_d(bh8_ctx* ctx, void* d_ptr, int value, size_t bytes);
  * sustained FP64 FLOP/s (FMA = 2) -- the roofline denominator for this path. */
 int bh8_measure_fp64_peak(bh8_ctx* ctx, double* flops_per_s, double* seconds_run);
 
+/* Precision study: geodesic updates per second of the bare update chain (no hit logic), in FP64 as
+ * the renderer runs it (fp32 = 0) or in FP32 (fp32 = 1).  See DESIGN.md 4.4. */
+int bh8_measure_stepping(bh8_ctx* ctx, int fp32, double* updates_per_s);
+
 size_t bh8_pixel_bytes(int pixel_format);
 /* Bytes that travel host -> device per frame: the frame constants derived from the snapshot, passed as
  * kernel parameters (there is no other per-frame input). */
