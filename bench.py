@@ -218,6 +218,98 @@ def bench_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def bench_8k_stripes(args, r, base, rank, world, flags):
+    """BASELINE configs[4]: ONE 7680x4320 frame at nstep 200, sharded WITHIN the frame: interleaved
+    16-row stripes dealt round-robin to the ranks (sharding.stripe_rows_of), every rank's kernel
+    storing its stripes straight into GPU 0's frame buffer (IPC mapping, NVLink).  Strong scaling:
+    the work per step is fixed, so value = rays of one frame / (max over ranks of the kernel time)."""
+    import torch
+    import torch.distributed as dist
+    from blackhole_8_b200 import abi
+    W, H, nstep, stripe = 7680, 4320, 200, 16
+    snap = base.with_resolution(W, H)
+    frame_bytes = W * H * 4
+    handle = [None]
+    if rank == 0:
+        buf = r.frame_alloc(frame_bytes)
+        handle[0] = r.ipc_export(buf) if world > 1 else None
+    if world > 1:
+        dist.broadcast_object_list(handle, src=0)
+        if rank != 0:
+            buf = r.ipc_import(handle[0])
+    flush_bytes = 256 << 20
+    flush = r.frame_alloc(flush_bytes)
+    kw = dict(nstep=nstep, flags=flags, stripe_rows=stripe, shard_index=rank, shard_count=world)
+    steps = max(3, min(args.steps, 20))
+    r.render_device(snap, buf, **dict(kw, flags=flags | abi.FLAG_STATS))
+    r.sync()
+    st = r.read_stats()
+    cnt = torch.tensor([st.rays, st.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cnt)
+    launches0 = r.launches
+    for _ in range(3):
+        r.render_device(snap, buf, **kw)
+    r.sync()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    kernel_ms = 0.0
+    for i in range(steps):
+        r.memset_d(flush, i & 0xFF, flush_bytes)
+        r.timer_begin()
+        r.render_device(snap, buf, **kw)
+        kernel_ms += r.timer_end_ms()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = r.launches - launches0 - 3
+    # end to end: all ranks render their stripes, then rank 0 reads the gathered frame back
+    pinned = r.pinned((H, W, 4)) if rank == 0 else None
+    e2e_steps = 3
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r.render_device(snap, buf, **kw)
+        r.sync()
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            r.memcpy_d2h(pinned.array, buf)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([kernel_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kernel_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        return
+    ms = kernel_ms / steps
+    rays = W * H
+    peak, _ = r.measure_fp64_peak()
+    n_extra = max(0, base.scene.n_obj - 2)
+    flops = (FLOPS_PER_STEP_BASE + FLOPS_PER_EXTRA_OBJECT * n_extra) * cnt[1].item() + FLOPS_SETUP * cnt[0].item()
+    print(json.dumps({
+        "metric": "Mrays/s", "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": steps,
+        "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg4: one 7680x4320 frame, cfg1 scene, nstep 200, interleaved %d-row stripes over the "
+                               "ranks, stores into GPU 0's IPC-mapped frame" % stripe,
+                   "rays_per_step": rays, "steps_per_ray": cnt[1].item() / cnt[0].item(),
+                   "l2": "flushed between steps by a 256 MiB memset outside the per-step CUDA-event pair"},
+        "frames_per_s": 1e3 / ms, "gsteps_per_s": cnt[1].item() / (ms * 1e-3) / 1e9, "clocks": clocks,
+        "e2e": {"value": rays * e2e_steps / e2e_s / 1e6, "unit": "Mrays/s",
+                "h2d_bytes_per_step": int(r.lib.bh8_launch_param_bytes()) * world, "d2h_bytes_per_step": frame_bytes,
+                "what": "all ranks render their stripes into GPU 0, barrier, rank 0 copies the 133 MB frame to pinned host memory"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "fp64", "achieved": flops / world / (ms * 1e-3) / 1e12, "peak": peak / 1e12,
+                     "unit": "TFLOP/s", "frac": flops / world / (ms * 1e-3) / peak, "traffic": None,
+                     "note": "per GPU: algorithmic flops of its stripes / kernel time"},
+        "cpu_baseline": None,
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -227,7 +319,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batching", action="store_true")
     ap.add_argument("--workload", default="cfg1_spin",
-                    choices=["cfg1_spin", "cfg3_flythrough", "cfg1_static", "cfg10_flat"],
+                    choices=["cfg1_spin", "cfg3_flythrough", "cfg1_static", "cfg10_flat", "cfg4_8k"],
                     help="frame sequence: configs[1] with the disc spinning frame to frame as in the "
                          "reference's loop (default), the configs[3] fly-through, or configs[1] frame 0 only")
     args = ap.parse_args()
@@ -260,6 +352,12 @@ def main():
     r = Renderer((local_rank,))
     r.set_textures(base, load_texture)
     flags = abi.FLAG_NO_BATCHING if args.no_batching else 0
+    if args.workload == "cfg4_8k":
+        bench_8k_stripes(args, r, base, rank, world, flags)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # Frames are whole units of work: step i of the job renders frames i*world .. i*world+world-1 of
     # the sequence and rank r owns frame i*world + r (sharding.frames_of) -- the same workload at every

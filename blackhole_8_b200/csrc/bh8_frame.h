@@ -60,6 +60,8 @@ struct Bh8Frame {
   double u_horizon;     // horizon sphere cannot be reached while u <= u_horizon and |dphi| <= 1
   uint32_t noncentral_mask;  // objects handled by the side-sign filter
   uint32_t central_mask;     // objects handled by the phi-crossing filter
+  uint32_t hole_mask;        // BH8_KIND_BLACKHOLE objects (the horizon sphere)
+  int32_t central_obj0;      // index of the first central plane (the only one when n_central == 1)
   int32_t first_resolve;     // 1: always resolve the first segment exactly (camera too close / in a plane)
   int32_t n_nc;              // number of non-central planes (<= BH8_MAX_OBJECTS)
   int32_t nc_obj[BH8_MAX_OBJECTS];  // their object indices, in scene order
@@ -184,6 +186,7 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
     switch (o->kind) {
       case BH8_KIND_BLACKHOLE:
         q->cls = BH8_CLASS_HORIZON;
+        f->hole_mask |= 1u << k;
         if (k != scene->bh_index)
           BH8_FAIL(BH8_EUNSUPPORTED, "more than one black hole in a scene is not supported");
         for (int i = 0; i < 3; ++i) q->p0[i] = o->v[0][i];
@@ -256,6 +259,7 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
     const double side_cam = bh8h_dot(q->n, wc);
     if (side_cam == 0) f->first_resolve = 1;
     if (q->central) {
+      if (f->n_central == 0) f->central_obj0 = k;
       f->central_mask |= 1u << k;
       f->n_central++;
     } else {
