@@ -17,7 +17,8 @@
 //   cfg 6-9  stress scenes for the GPU path's rarely taken branches (not BASELINE configs):
 //          6 hole moved off the disc's plane (arrow keys, blackhole_solution_test.cc:391-396) and
 //            camera tilted; 7 camera turned away from the hole (mirrored-start rays, the atan quirk);
-//          8 more planes than the kernel has filter slots; 9 camera inside the photon sphere
+//          8 more planes than the kernel has filter slots; 9 camera inside the photon sphere;
+//          11 exactly four filtered planes
 //   cfg 10 the flat-space scene of ray_tracer_test.cc:45-98 (800x450, 3 textured rectangles + chess
 //          floor, no hole), frame k after k rounds of its object animation (:237-261)
 //
@@ -197,6 +198,17 @@ inline Scene* Build(int cfg, int width, int height, int frame, const std::string
       AddRectangle(s, m, texdir, "winter.jpg", 300, -300, 500, 300, -600, 500, 300, -600, 200, 300, -300, 200);
       AddRectangle(s, m, texdir, "karina.jpeg", -200, -400, 300, 0, -400, 300, 0, -400, 0, -200, -400, 0);
       AddChess(s, m, 25);
+      AddBlackhole(s, m, 10);
+      break;
+    case 11:  // exactly four planes off the hole's centre (the kernel's largest filtered instantiation)
+      s = new Scene(width, height, blackhole::pi / 2);
+      s->camera.MoveTo(-1200, 200, 300);
+      s->camera.RotateZ(0.15);
+      AddDisc(s, m, texdir);
+      AddBackground(s, m, texdir);
+      AddRectangle(s, m, texdir, "mooni.jpeg", -400, 300, 350, -400, 100, 350, -400, 100, 150, -400, 300, 150);
+      AddRectangle(s, m, texdir, "winter.jpg", 300, -300, 500, 300, -600, 500, 300, -600, 200, 300, -300, 200);
+      AddRectangle(s, m, texdir, "karina.jpeg", -200, -400, 300, 0, -400, 300, 0, -400, 0, -200, -400, 0);
       AddBlackhole(s, m, 10);
       break;
     case 9:  // camera at r = 25.5 < 3M: du < 0, every segment takes the exact path

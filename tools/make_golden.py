@@ -40,6 +40,7 @@ SMALL = {
     "cfg7_lookaway_400x225": (7, 400, 225, 0, None),
     "cfg8_manyplanes_400x225": (8, 400, 225, 0, None),
     "cfg9_inside_320x180": (9, 320, 180, 0, None),
+    "cfg11_fourplanes_400x225": (11, 400, 225, 0, None),
     "cfg1_nstep2_320x180": (1, 320, 180, 0, 2),
     "cfg1_tiny_5x3": (1, 5, 3, 0, None),
     # flat space: the ray_tracer_test.cc scene; frame 0 == the UNCHANGED ray_tracer_test's frame
