@@ -67,6 +67,9 @@ struct Bh8Frame {
   int32_t nc_obj[BH8_MAX_OBJECTS];  // their object indices, in scene order
   float nc_nF[BH8_MAX_OBJECTS];     // float(n . Fhat)
   float nc_c[BH8_MAX_OBJECTS];      // float(c_bh)
+  // leases of filter (2), see lane_update: 0.4995 / max|n_j| and 0.24975 / max|c_bh_j| over the
+  // non-central planes (the margin is split between the phi and the u movement, 0.1 % kept back)
+  float lease_kphi, lease_ku;
   uint32_t nc_cam_bits;      // side of the camera w.r.t. non-central plane j: bit j = positive, bit 16+j = negative
   int32_t resolve_wait;      // warp iterations a pending exact test may wait for company (batching window)
   // output
@@ -175,7 +178,7 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
   if (f->shard_count > 1 && (f->shard_index < 0 || f->shard_index >= f->shard_count || f->stripe_rows < 1))
     BH8_FAIL(BH8_EINVAL, "bad stripe sharding parameters");
 
-  double min_dist = INFINITY;
+  double min_dist = INFINITY, max_n = 0.0, max_c = 0.0;
   for (int k = 0; k < scene->n_obj; ++k) {
     const bh8_object* o = &scene->obj[k];
     Bh8Obj* q = &f->obj[k];
@@ -270,9 +273,15 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
       f->nc_c[j] = (float)q->c_bh;
       if (side_cam > 0) f->nc_cam_bits |= 1u << j;
       if (side_cam < 0) f->nc_cam_bits |= 1u << (16 + j);
-      if (fabs(q->c_bh) < min_dist) min_dist = fabs(q->c_bh);
+      const double nn = sqrt(bh8h_dot(q->n, q->n));  // 1 for the reference's shapes; not relied upon
+      if (!(nn > 0)) BH8_FAIL(BH8_EINVAL, "plane with a zero normal");
+      if (fabs(q->c_bh) / nn < min_dist) min_dist = fabs(q->c_bh) / nn;
+      if (nn > max_n) max_n = nn;
+      if (fabs(q->c_bh) > max_c) max_c = fabs(q->c_bh);
     }
   }
+  f->lease_kphi = f->noncentral_mask ? (float)(0.4995 / max_n) : 0.0f;
+  f->lease_ku = f->noncentral_mask ? (float)(0.24975 / max_c) : 0.0f;
   // A chord between two points of the ray stays inside radius max(r1,r2); a plane at distance D
   // from the hole can only be met when max(r1,r2) >= D, i.e. min(u1,u2) <= 1/D (small margin).
   f->u_gate = f->noncentral_mask ? (1.0 + 1e-9) / min_dist : -1.0;

@@ -8,7 +8,15 @@
 #include <cmath>
 #include <cstring>
 
+#define BH8_HOST_COUNTERS 1
+static unsigned long long bh8_host_filter_evaluations = 0;  // bumped by side_filter()
 #include "bh8_ray.cuh"
+
+extern "C" unsigned long long bh8_harness_take_filter_evaluations() {
+  const unsigned long long n = bh8_host_filter_evaluations;
+  bh8_host_filter_evaluations = 0;
+  return n;
+}
 
 struct HarnessTexture {
   const uint8_t* bgr;

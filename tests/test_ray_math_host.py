@@ -56,6 +56,8 @@ def harness_render(snap, nstep=None, filter_slots=4):
                               counters, err)
     assert rc == 0, err.value
     out["updates"], out["exact_tests"] = int(counters[0]), int(counters[1])
+    L.bh8_harness_take_filter_evaluations.restype = C.c_ulonglong
+    out["filter_evaluations"] = int(L.bh8_harness_take_filter_evaluations())
     return out
 
 
