@@ -31,7 +31,7 @@ constexpr int kTileW = 32;
 #endif
 constexpr int kTileH = BH8_TILE_H;
 constexpr int kThreads = kTileW * kTileH;
-constexpr int kMaxFilterPlanes = 4;
+constexpr int kMaxFilterPlanes = kMaxFilterSlots;
 #ifndef BH8_UPDATES_PER_VOTE
 #define BH8_UPDATES_PER_VOTE 2  // geodesic updates between two rounds of warp votes
 #endif
@@ -60,77 +60,47 @@ struct DeviceFetch {
   }
 };
 
-// Register budget.  The stepping loop needs ~45 registers, the exact segment test ~110.  Letting the
-// second set the kernel's register count would halve the occupancy that hides the FP64 pipe's
-// latency, so a lane that enters the exact test first parks its state in its mailbox (shared
-// memory) and re-loads it afterwards: no stepping value is live inside the test, and the test is
-// entered about once per ray.  (volatile: the compiler must not forward the stores to the loads,
-// which would keep the values alive in registers.)
-// Mailbox, stride kThreads.  doubles: bh8::Mail's slots [0..6] (e2 / hit point, and the frozen lane's
-// delta, t, phi_trig, du_h), then [7] u, [8] phi, [9] dphi_prev, [10] binv2.  ints: Mail's [0] span,
-// then [1] i, [2] next_evt, [3] state, [4] fbits, [5] fstep, [6] steps, [7] hit_obj, [8] flags,
-// [9] gate_in, [10] gate_out, [11] lo, [12..] fa/fb bit patterns.  binv2, flags, gates, lo, fa/fb
-// never change after setup: written once.
+// Register budget.  The stepping loop needs ~40 registers, the exact segment test ~110.  Letting the
+// second set the kernel's register count would halve the occupancy, so (a) everything only the rare
+// paths use lives in the ray's mailbox in shared memory to begin with (bh8::Mail), and (b) a lane
+// that enters the exact test first parks the few stepping values it holds in registers and
+// re-loads them afterwards: no stepping value is live inside the test, and the test is entered
+// about once per ray.  (volatile: the compiler must not forward the stores to the loads, which
+// would keep the values alive in registers.)
+// Mailbox, stride kThreads: bh8::Mail's slots, then doubles u, phi, dphi_prev, binv2 and ints i,
+// state, lo of a parked lane (binv2 and lo are written once: a frozen lane always has its base lo).
 constexpr int kMailDoubles = kMailDoublesRay + 4;
-constexpr int kMailInts = kMailIntsRay + 11 + 2 * kMaxFilterPlanes;
+constexpr int kMailInts = kMailIntsRay + 3;
 enum : int { kKdU = kMailDoublesRay, kKdPhi, kKdDphi, kKdBinv2 };
-enum : int { kKwI = kMailIntsRay, kKwNext, kKwState, kKwFbits, kKwFstep, kKwSteps, kKwHit, kKwFlags, kKwGateIn,
-             kKwGateOut, kKwLo, kKwFab };
+enum : int { kKwI = kMailIntsRay, kKwState, kKwLo };
 
 template <int NN>
-__device__ __forceinline__ void lane_park_constants(const Lane<NN>& L, volatile double* md, volatile int* mi) {
-  md[kKdBinv2 * kThreads] = L.binv2;
-  mi[kKwFlags * kThreads] = L.flags;
-  mi[kKwGateIn * kThreads] = L.gate_in;
-  mi[kKwGateOut * kThreads] = L.gate_out;
-  mi[kKwLo * kThreads] = L.lo;
-#pragma unroll
-  for (int j = 0; j < (NN > 0 ? NN : 0); ++j) {
-    mi[(kKwFab + 2 * j) * kThreads] = __float_as_int(L.fa[j]);
-    mi[(kKwFab + 2 * j + 1) * kThreads] = __float_as_int(L.fb[j]);
-  }
+__device__ __forceinline__ void lane_park_constants(const Lane<NN>& L, const Mail m) {
+  m.set_d(kKdBinv2, L.binv2);
+  m.set_w(kKwLo, L.lo);
 }
 
 // What a frozen lane still carries in registers and the exact test needs or changes.
 template <int NN>
-__device__ __forceinline__ void lane_park(const Lane<NN>& L, volatile double* md, volatile int* mi) {
-  md[kKdU * kThreads] = L.u;
-  md[kKdPhi * kThreads] = L.phi;
-  md[kKdDphi * kThreads] = L.dphi_prev;
-  mi[kKwI * kThreads] = L.i;
-  mi[kKwNext * kThreads] = L.next_evt;
-  mi[kKwState * kThreads] = L.state;
-  mi[kKwFbits * kThreads] = (int)L.fbits;
-  mi[kKwFstep * kThreads] = L.fstep;
-  mi[kKwSteps * kThreads] = L.steps;
-  mi[kKwHit * kThreads] = L.hit_obj;
+__device__ __forceinline__ void lane_park(const Lane<NN>& L, const Mail m) {
+  m.set_d(kKdU, L.u);
+  m.set_d(kKdPhi, L.phi);
+  m.set_d(kKdDphi, L.dphi_prev);
+  m.set_w(kKwI, L.i);
+  m.set_w(kKwState, L.state);
 }
 
 // Re-load a lane from its mailbox: frozen (as lane_freeze leaves it) or, if the exact test cleared
 // the segment (state kRun), travelling again with the values the test left in Mail's slots.
 template <int NN>
-__device__ __forceinline__ void lane_unpark(Lane<NN>& L, const Mail m, const volatile double* md,
-                                            const volatile int* mi) {
-  L.u = md[kKdU * kThreads];
-  L.phi = md[kKdPhi * kThreads];
-  L.dphi_prev = md[kKdDphi * kThreads];
-  L.binv2 = md[kKdBinv2 * kThreads];
-  L.i = mi[kKwI * kThreads];
-  L.next_evt = mi[kKwNext * kThreads];
-  L.state = mi[kKwState * kThreads];
-  L.fbits = (uint32_t)mi[kKwFbits * kThreads];
-  L.fstep = mi[kKwFstep * kThreads];
-  L.steps = mi[kKwSteps * kThreads];
-  L.hit_obj = mi[kKwHit * kThreads];
-  L.flags = mi[kKwFlags * kThreads];
-  L.gate_in = mi[kKwGateIn * kThreads];
-  L.gate_out = mi[kKwGateOut * kThreads];
-  L.lo = mi[kKwLo * kThreads];
-#pragma unroll
-  for (int j = 0; j < (NN > 0 ? NN : 0); ++j) {
-    L.fa[j] = __int_as_float(mi[(kKwFab + 2 * j) * kThreads]);
-    L.fb[j] = __int_as_float(mi[(kKwFab + 2 * j + 1) * kThreads]);
-  }
+__device__ __forceinline__ void lane_unpark(Lane<NN>& L, const Mail m) {
+  L.u = m.get_d(kKdU);
+  L.phi = m.get_d(kKdPhi);
+  L.dphi_prev = m.get_d(kKdDphi);
+  L.binv2 = m.get_d(kKdBinv2);
+  L.i = m.get_w(kKwI);
+  L.state = m.get_w(kKwState);
+  L.lo = m.get_w(kKwLo);
   L.bgr = 0;
   L.oob = 0;
   L.t = 0.0;
@@ -235,19 +205,21 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
   // ---- trace ----------------------------------------------------------------------------------
   __shared__ double sh_md[kMailDoubles * kThreads];
   __shared__ int sh_mi[kMailInts * kThreads];
-  double* const md = sh_md + tid;
-  int* const mi = sh_mi + tid;
-  const Mail mail{md, mi, kThreads};
+  Mail mail;
+#if defined(__CUDA_ARCH__)
+  mail.d = (uint32_t)__cvta_generic_to_shared(sh_md + tid);
+  mail.w = (uint32_t)__cvta_generic_to_shared(sh_mi + tid);
+  asm volatile("" : "+r"(mail.d), "+r"(mail.w));  // opaque: two registers, never re-derived
+#else
+  mail.d = sh_md + tid;  // (nvcc's host pass only parses this)
+  mail.w = sh_mi + tid;
+#endif
+  mail.stride = kThreads;
   Lane<NN> L;
   lane_inert(L);
-  L.flags = 0;
-  L.hit_obj = -1;
-  L.steps = 0;
-  L.bgr = 0;
-  L.oob = 0;
   if (inside) {
     lane_setup(f, x, y, L, mail);
-    lane_park_constants(L, md, mi);
+    lane_park_constants(L, mail);
   }
   int waited = 0;
   for (;;) {
@@ -266,29 +238,28 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
     if (runs != 0u && ++waited <= f.resolve_wait) continue;
     waited = 0;
     if ((unsigned)(L.state - kPend) < 2u) {
-      lane_park(L, md, mi);
+      lane_park(L, mail);
       {
         Lane<NN> T;  // the test works on its own copy, loaded from the mailbox
-        lane_unpark(T, mail, md, mi);
+        lane_unpark(T, mail);
         lane_exact(f, T, mail);
         if (T.state == kPendChord) lane_exact(f, T, mail);  // event right after a cleared segment
         if (T.state == kRun) lane_freeze(T, mail, kRun);    // hand the thawed values over through Mail
-        lane_park(T, md, mi);
+        lane_park(T, mail);
       }
-      lane_unpark(L, mail, md, mi);
+      lane_unpark(L, mail);
     }
   }
-  const int steps = L.steps;
+  const int steps = inside ? mail.get_w(kMwSteps) : 0;
+  const int hit_obj = inside ? mail.get_w(kMwHit) : -1;
 
   // ---- colour ------------------------------------------------------------------------------------
-  if (!inside) L.hit_obj = -1;
-  L.oob = 0;
-  lane_shade(f, L, mail, DeviceFetch{tex});
+  lane_shade(f, L, mail, hit_obj, DeviceFetch{tex});
   const uint32_t bgr = L.bgr, oob = L.oob;
   int cls = BH8_CLASS_BACKGROUND, key = -1;
-  if (inside && L.hit_obj >= 0) {
-    cls = f.obj[L.hit_obj].cls;
-    key = f.obj[L.hit_obj].key;
+  if (hit_obj >= 0) {
+    cls = f.obj[hit_obj].cls;
+    key = f.obj[hit_obj].key;
   }
   store_pixel(f, out, sh_rgba, sh_red, tid, lane, slot, x0, y0, x, y, inside, bgr, oob, cls, key, steps);
 }

@@ -57,12 +57,13 @@ static void trace_frame(const Bh8Frame& f, const HostFetch& fetch, uint8_t* out_
         }
       }
       for (int k = 0; k < g_frozen_updates; ++k) bh8::lane_update(f, L, mail);  // ended rays too
-      bh8::lane_shade(f, L, mail, fetch);
+      const int hit_obj = mail.get_w(bh8::kMwHit);
+      bh8::lane_shade(f, L, mail, hit_obj, fetch);
       const uint32_t bgr = L.bgr;
       int cls = BH8_CLASS_BACKGROUND, key = -1;
-      if (L.hit_obj >= 0) {
-        cls = f.obj[L.hit_obj].cls;
-        key = f.obj[L.hit_obj].key;
+      if (hit_obj >= 0) {
+        cls = f.obj[hit_obj].cls;
+        key = f.obj[hit_obj].key;
       }
       const size_t i = static_cast<size_t>(y) * f.width + x;
       out_bgr[3 * i] = bgr & 255;
@@ -70,7 +71,7 @@ static void trace_frame(const Bh8Frame& f, const HostFetch& fetch, uint8_t* out_
       out_bgr[3 * i + 2] = (bgr >> 16) & 255;
       out_class[i] = (uint8_t)cls;
       out_key[i] = (int8_t)key;
-      out_steps[i] = (uint16_t)L.steps;
+      out_steps[i] = (uint16_t)mail.get_w(bh8::kMwSteps);
     }
   }
 }
