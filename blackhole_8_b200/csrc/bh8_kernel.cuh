@@ -86,7 +86,7 @@ __device__ __forceinline__ void lane_park(const Lane<NN>& L, const Mail m) {
   m.set_d(kKdU, L.u);
   m.set_d(kKdPhi, L.phi);
   m.set_d(kKdDphi, L.dphi_prev);
-  m.set_w(kKwI, L.i);
+  m.set_w(kKwI, L.idx());
   m.set_w(kKwState, L.state);
 }
 
@@ -98,9 +98,9 @@ __device__ __forceinline__ void lane_unpark(Lane<NN>& L, const Mail m) {
   L.phi = m.get_d(kKdPhi);
   L.dphi_prev = m.get_d(kKdDphi);
   L.binv2 = m.get_d(kKdBinv2);
-  L.i = m.get_w(kKwI);
   L.state = m.get_w(kKwState);
   L.lo = m.get_w(kKwLo);
+  L.set_idx(m.get_w(kKwI));
   L.bgr = 0;
   L.oob = 0;
   L.t = 0.0;
@@ -227,8 +227,8 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
     // lane_freeze), a few updates per round of warp votes.
 #pragma unroll
     for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k) lane_update(f, L, mail);
-    const unsigned runs = __ballot_sync(0xffffffffu, L.state == kRun);
-    const unsigned pend = __ballot_sync(0xffffffffu, (unsigned)(L.state - kPend) < 2u);
+    const unsigned present = __reduce_or_sync(0xffffffffu, (unsigned)L.state);
+    const unsigned runs = present & kRun, pend = present & (kPend | kPendChord);
     if (pend == 0u) {
       if (runs == 0u) break;  // every ray of the patch has ended
       continue;
@@ -237,7 +237,7 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
     // waited resolve_wait rounds; then all of them run together.
     if (runs != 0u && ++waited <= f.resolve_wait) continue;
     waited = 0;
-    if ((unsigned)(L.state - kPend) < 2u) {
+    if (L.state & (kPend | kPendChord)) {
       lane_park(L, mail);
       {
         Lane<NN> T;  // the test works on its own copy, loaded from the mailbox

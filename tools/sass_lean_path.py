@@ -32,7 +32,7 @@ def main():
     verbose = "-v" in sys.argv
     ins = load(so, nn)
     index = {a: k for k, (a, _) in enumerate(ins)}
-    votes = [k for k, (_, t) in enumerate(ins) if "VOTE" in t]
+    votes = [k for k, (_, t) in enumerate(ins) if "VOTE" in t or "REDUX" in t]
     first_vote = votes[0]
     head = first_vote  # the shortest cycle through the first vote is one lean loop iteration
 
