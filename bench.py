@@ -342,7 +342,11 @@ def main():
     build()
     args.warmup = max(args.warmup, 3)
     torch.cuda.set_device(local_rank)
+    numa_cpus = None
     if world > 1:
+        from blackhole_8_b200.sharding import bind_to_gpu_numa
+        if not os.environ.get("BH8_NO_NUMA_BIND"):
+            numa_cpus = bind_to_gpu_numa(local_rank)  # before any pinned allocation (first touch)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -546,6 +550,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(r.lib.bh8_launch_param_bytes()) * world,
                 "d2h_bytes_per_step": frame_bytes * world, "steps": e2e_steps,
                 "frames_per_s": world * e2e_steps / e2e_s, "frame_ok": frame_ok,
+                "host_placement": ("rank 0 bound to %d CPUs next to its GPU (NVML affinity), every rank likewise"
+                                   % len(numa_cpus)) if numa_cpus else "as launched",
                 "what": "bh8_submit()/bh8_wait(): snapshot -> kernel parameters, RGBA8 frame read back into pinned "
                         "host memory, two frames in flight (copy of frame k overlaps kernel of frame k+1), wall clock",
                 "synchronous_bh8_render": {"value": e2e_sync_value, "unit": "Mrays/s",

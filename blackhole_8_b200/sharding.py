@@ -37,3 +37,27 @@ def stripe_rows_of(height, stripe_rows, rank, world):
 def ring_slot_offset(step, rank, world, slots, frame_bytes):
     """Byte offset of rank's frame for `step` inside GPU 0's frame ring (slots x world frames)."""
     return ((step % slots) * world + rank) * frame_bytes
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPU cores next to GPU `device_index` (NVML's ideal CPU affinity).
+
+    One process per GPU reads its frames back into pinned host memory; with first-touch placement
+    the pinned pages land on the NUMA node the process runs on, so a process that runs on the other
+    socket sends every frame across the inter-socket link.  Returns the CPU set it bound to, or None
+    when NVML is not available or reports nothing usable (the process is then left where it is)."""
+    import os
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        handle = nv.nvmlDeviceGetHandleByIndex(device_index)
+        n_cpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # no NVML / not permitted: placement stays as the launcher chose it
+        return None
