@@ -109,7 +109,7 @@ __device__ __forceinline__ void lane_unpark(Lane<NN>& L, const Mail m) {
   } else {
     L.delta = 0.0;
     L.du_h = 0.0;
-    L.phi_trig = INFINITY;
+    L.trig_hi = kTrigNever;
     L.span = 0xffffffffu;
     L.inc = 0;
   }
