@@ -103,13 +103,13 @@ __device__ __forceinline__ void lane_unpark(Lane<NN>& L, const Mail m) {
   L.set_idx(m.get_w(kKwI));
   L.bgr = 0;
   L.oob = 0;
-  L.t = 0.0;
   if (L.state == kRun) {
     lane_thaw(L, m);
   } else {
     L.delta = 0.0;
     L.du_h = 0.0;
     L.trig_hi = kTrigNever;
+    L.t_thr = kTrigNever;
     L.span = 0xffffffffu;
     L.inc = 0;
   }
