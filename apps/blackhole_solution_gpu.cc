@@ -6,12 +6,14 @@
 // CUDA renderer.  Headless: runs a scripted number of frames instead of reading keys.
 //
 //   blackhole_solution_gpu [--cfg N] [--width W] [--height H] [--frames K] [--nstep S]
-//                          [--texdir DIR] [--out PREFIX]
-// Writes PREFIX_<frame>.bgr (raw: int32 rows, int32 cols, BGR bytes) when --out is given.
+//                          [--texdir DIR] [--out PREFIX] [--video FILE.avi]
+// Writes PREFIX_<frame>.bgr (raw: int32 rows, int32 cols, BGR bytes) when --out is given, and a
+// Motion-JPEG AVI (the reference's video.avi, :71-72; frames encoded on the GPU) when --video is.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <memory>
 #include <string>
 
 #include "blackhole/gpu/renderer.h"
@@ -19,7 +21,7 @@
 
 int main(int argc, char** argv) {
   int cfg = 0, width = 960, height = 540, frames = 1, nstep = -1;
-  std::string texdir = "build/textures", out;
+  std::string texdir = "build/textures", out, video;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -30,6 +32,7 @@ int main(int argc, char** argv) {
     else if (a == "--nstep") nstep = std::atoi(next());
     else if (a == "--texdir") texdir = next();
     else if (a == "--out") out = next();
+    else if (a == "--video") video = next();
     else {
       std::fprintf(stderr, "unknown argument %s\n", a.c_str());
       return 2;
@@ -45,10 +48,13 @@ int main(int argc, char** argv) {
 
   try {
     blackhole::gpu::Renderer gpu;
+    std::unique_ptr<blackhole::gpu::VideoWriter> out_capture;
+    if (!video.empty()) out_capture.reset(new blackhole::gpu::VideoWriter(&gpu, video, width, height, 29));
     cv::Mat screen;
     for (int k = 0; k < frames; ++k) {
       const auto t1 = std::chrono::high_resolution_clock::now();
-      gpu.Render(manager, *scene->blackhole, scene->camera, &screen, nstep);
+      if (out_capture) out_capture->Write(manager, *scene->blackhole, scene->camera, nstep);
+      if (!out_capture || !out.empty()) gpu.Render(manager, *scene->blackhole, scene->camera, &screen, nstep);
       const auto t2 = std::chrono::high_resolution_clock::now();
       const auto us = std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
       std::cout << "Took " << us / 1000.0 << "ms (kernel " << gpu.last_stats().kernel_ms << "ms, "
@@ -65,6 +71,7 @@ int main(int argc, char** argv) {
       }
       if (scene->disc) scene->disc->RotateZ(blackhole::pi / 180);
     }
+    if (out_capture) std::cout << "video: " << out_capture->Release() << " bytes\n";
   } catch (const std::exception& e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

@@ -310,6 +310,49 @@ def bench_8k_stripes(args, r, base, rank, world, flags):
     }))
 
 
+def measure_sink(r, seq, W, H, frames=120, quality=95):
+    """SURVEY 8f-2, reported beside the headline: frames/s of the GPU frame sink (bh8_sink_render: trace the
+    frame, JPEG-encode it on the device with nvJPEG, only the bitstream comes to the host) -- what the
+    reference's `out_capture.write(frame)` becomes -- next to OpenCV's own JPEG encoder on one host core,
+    which is what cv::VideoWriter(MJPG) spends per frame.  Not part of value / e2e."""
+    try:
+        import cv2
+        from blackhole_8_b200 import abi
+        from blackhole_8_b200.renderer import VideoSink
+        sink = VideoSink(r, None, W, H, fps=29, quality=quality)
+        for i in range(5):
+            sink.render(seq[i % len(seq)])
+        before = sink.stats()
+        t0 = time.perf_counter()
+        for i in range(frames):
+            sink.render(seq[i % len(seq)])
+        dt = time.perf_counter() - t0
+        st = sink.stats()
+        jpg = sink.last_jpeg()
+        sink.close()
+        frame = r.render(seq[(frames - 1) % len(seq)], pixel_format=abi.PIXEL_BGR8)["pixels"][0]
+        dec = cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_COLOR)
+        mse = float(np.mean((dec.astype(np.float64) - frame.astype(np.float64)) ** 2))
+        n_cpu = 8
+        t0 = time.perf_counter()
+        for _ in range(n_cpu):
+            ok, enc = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_QUALITY, quality])
+        cpu_dt = time.perf_counter() - t0
+        ref = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+        mse_cpu = float(np.mean((ref.astype(np.float64) - frame.astype(np.float64)) ** 2))
+        n = st["frames"] - before["frames"]
+        return {"what": "bh8_sink_render: render + nvJPEG encode (4:2:0, quality %d) on the GPU, bitstream to host" % quality,
+                "frames_per_s": n / dt, "Mrays_per_s": n * W * H / dt / 1e6,
+                "jpeg_bytes_per_frame": (st["jpeg_bytes"] - before["jpeg_bytes"]) / n,
+                "raw_bytes_per_frame": W * H * 3,
+                "nvjpeg_device_ms_per_frame": (st["encode_ms"] - before["encode_ms"]) / n,
+                "psnr_db": 10.0 * np.log10(255.0 ** 2 / mse) if mse > 0 else 99.0,
+                "host_opencv_imencode": {"frames_per_s": n_cpu / cpu_dt, "cores": 1, "bytes_per_frame": len(enc),
+                                         "psnr_db": 10.0 * np.log10(255.0 ** 2 / mse_cpu) if mse_cpu > 0 else 99.0}}
+    except Exception as e:  # the sink is an extra: never fail the headline line over it
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -491,6 +534,8 @@ def main():
             dist.destroy_process_group()
         return
 
+    sink = measure_sink(r, seq, W, H) if world == 1 else None
+
     # ---- roofline: algorithmic FP64 flops / kernel time vs the DFMA peak measured now ----------
     n_extra = max(0, base.scene.n_obj - 2)
     hits = st.rays - st.class_count[0]
@@ -560,6 +605,8 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
+    if sink:
+        line["sink"] = sink
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

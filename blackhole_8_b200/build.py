@@ -39,7 +39,7 @@ def build(force=False, verbose=False, out=None, defines=()):
         return LIB
     out = out or LIB
     cmd = [nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + \
-        ["-I" + os.path.join(ROOT, "include"), "-I" + SRC, "-o", out, os.path.join(SRC, "bh8_lib.cu")]
+        ["-I" + os.path.join(ROOT, "include"), "-I" + SRC, "-o", out, os.path.join(SRC, "bh8_lib.cu"), "-lnvjpeg"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

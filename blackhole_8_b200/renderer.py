@@ -64,6 +64,14 @@ def load_library(path=None):
         "bh8_host_free": (i32, [vp]),
         "bh8_measure_fp64_peak": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "bh8_measure_stepping": (i32, [vp, i32, C.POINTER(C.c_double)]),
+        "bh8_sink_open": (i32, [vp, C.c_char_p, i32, i32, C.c_double, i32, C.POINTER(vp)]),
+        "bh8_sink_render": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params)]),
+        "bh8_sink_write_device": (i32, [vp, vp]),
+        "bh8_sink_append_jpeg": (i32, [vp, vp, C.c_size_t]),
+        "bh8_sink_last_jpeg": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "bh8_sink_stats": (i32, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_double)]),
+        "bh8_sink_last_error": (C.c_char_p, [vp]),
+        "bh8_sink_close": (i32, [vp, C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -255,3 +263,65 @@ class Renderer:
         f, s = C.c_double(), C.c_double()
         self._check(self.lib.bh8_measure_fp64_peak(self._ctx, C.byref(f), C.byref(s)))
         return f.value, s.value
+
+
+class VideoSink:
+    """Motion-JPEG AVI writer, the mirror of include/bh8.h's bh8_sink_* (SURVEY 8f-2): stands where the
+    reference's cv::VideoWriter(path, fourcc('M','J','P','G'), fps, size) stands
+    (blackhole_solution_test.cc:71-72,334).  With a Renderer the frames are encoded on the GPU
+    (nvJPEG) from the device-resident frame; with renderer=None it is a plain container for ready
+    JPEGs (no GPU needed)."""
+
+    def __init__(self, renderer, path, width, height, fps=29.0, quality=95):
+        self.lib = renderer.lib if renderer is not None else load_library()
+        self._renderer = renderer
+        self._h = C.c_void_p()
+        ctx = renderer._ctx if renderer is not None else None
+        rc = self.lib.bh8_sink_open(ctx, path.encode() if path else None, width, height, float(fps), int(quality),
+                                    C.byref(self._h))
+        if rc != 0:
+            raise Bh8Error(rc, (self.lib.bh8_last_error(ctx) or b"").decode())
+        self.width, self.height = width, height
+
+    def _check(self, rc):
+        if rc != 0:
+            raise Bh8Error(rc, (self.lib.bh8_sink_last_error(self._h) or b"").decode())
+
+    def render(self, snap, nstep=None, flags=0):
+        """Trace one frame on the GPU and append it (nothing but the bitstream leaves the device)."""
+        prm = snap.params(abi.PIXEL_BGR8, flags, nstep)
+        self._check(self.lib.bh8_sink_render(self._h, C.byref(snap.scene), C.byref(snap.camera), C.byref(prm)))
+
+    def write_device(self, d_bgr_frame):
+        self._check(self.lib.bh8_sink_write_device(self._h, C.c_void_p(d_bgr_frame)))
+
+    def append_jpeg(self, data):
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        self._check(self.lib.bh8_sink_append_jpeg(self._h, buf, len(data)))
+
+    def last_jpeg(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.lib.bh8_sink_last_jpeg(self._h, C.byref(p), C.byref(n)))
+        return C.string_at(p.value, n.value) if n.value else b""
+
+    def stats(self):
+        f, b, ms = C.c_uint64(), C.c_uint64(), C.c_double()
+        self._check(self.lib.bh8_sink_stats(self._h, C.byref(f), C.byref(b), C.byref(ms)))
+        return {"frames": f.value, "jpeg_bytes": b.value, "encode_ms": ms.value}
+
+    def close(self):
+        """Finish the file; returns its size in bytes (0 for a sink without a file)."""
+        if not self._h:
+            return 0
+        n = C.c_uint64()
+        rc = self.lib.bh8_sink_close(self._h, C.byref(n))
+        self._h = C.c_void_p()
+        if rc != 0:
+            raise Bh8Error(rc, "bh8_sink_close failed (write error on the AVI file)")
+        return n.value
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BH8_ABI_VERSION 2
+#define BH8_ABI_VERSION 3
 #define BH8_MAX_OBJECTS 16
 #define BH8_MAX_TEXTURES 16
 #define BH8_MAX_DEVICES 8
@@ -213,6 +213,32 @@ int bh8_measure_fp64_peak(bh8_ctx* ctx, double* flops_per_s, double* seconds_run
 /* Precision study: geodesic updates per second of the bare update chain (no hit logic), in FP64 as
  * the renderer runs it (fp32 = 0) or in FP32 (fp32 = 1).  See DESIGN.md 4.4. */
 int bh8_measure_stepping(bh8_ctx* ctx, int fp32, double* updates_per_s);
+
+/* ---- Frame sink ------------------------------------------------------------
+ * Replaces cv::VideoWriter(path, cv::VideoWriter::fourcc('M','J','P','G'), fps, size, true) and
+ * out_capture.write(frame) of blackhole_solution_test.cc:71-72,334: a Motion-JPEG AVI file whose
+ * frames are JPEG-encoded ON THE GPU (nvJPEG, 4:2:0, baseline Huffman) straight from the
+ * device-resident BGR8 frame, so only the bitstream crosses PCIe.
+ *   ctx != NULL: GPU sink on device 0 of the context.  ctx == NULL: host-only container that is fed
+ *                ready JPEGs with bh8_sink_append_jpeg() (no GPU needed).
+ *   avi_path:    file to write, or NULL to encode only (read each frame with bh8_sink_last_jpeg()).
+ * Errors: negative return, text from bh8_sink_last_error() (bh8_last_error(ctx) for bh8_sink_open). */
+typedef struct bh8_sink bh8_sink;
+int bh8_sink_open(bh8_ctx* ctx, const char* avi_path, int width, int height, double fps, int quality,
+                  bh8_sink** out);
+/* Render one frame (as bh8_render_device, pixel format forced to BGR8) into the sink's own device
+ * buffer, encode it and append it: the GPU form of "trace the frame; out_capture.write(frame)". */
+int bh8_sink_render(bh8_sink* sink, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* params);
+/* Encode and append a BGR8 frame that is already in device memory (H * W * 3 bytes, device 0). */
+int bh8_sink_write_device(bh8_sink* sink, const void* d_bgr_frame);
+int bh8_sink_append_jpeg(bh8_sink* sink, const uint8_t* jpeg, size_t bytes);
+/* Bitstream of the most recent frame; valid until the next call on this sink. */
+int bh8_sink_last_jpeg(bh8_sink* sink, const uint8_t** data, size_t* bytes);
+/* Frames so far, their JPEG bytes, and the device time nvJPEG took for them (CUDA events, ms). */
+int bh8_sink_stats(const bh8_sink* sink, uint64_t* frames, uint64_t* jpeg_bytes, double* encode_ms);
+const char* bh8_sink_last_error(const bh8_sink* sink);
+/* Finish the AVI (index, sizes), release everything; the handle is invalid afterwards. */
+int bh8_sink_close(bh8_sink* sink, uint64_t* file_bytes);
 
 size_t bh8_pixel_bytes(int pixel_format);
 /* Bytes that travel host -> device per frame: the frame constants derived from the snapshot, passed as

@@ -91,6 +91,51 @@ class Renderer {
   bh8_ctx* ctx_ = nullptr;
   bh8_stats stats_{};
   std::vector<const unsigned char*> uploaded_;
+  friend class VideoWriter;
+};
+
+// Stands where the reference's cv::VideoWriter out_capture(save_dir/"video.avi",
+// fourcc('M','J','P','G'), 29, size, true) stands (blackhole_solution_test.cc:71-72): a Motion-JPEG
+// AVI, but the frames are traced AND JPEG-encoded on the GPU -- Write() replaces the pixel loop
+// plus out_capture.write(*buf) (:161-308, :334); only the bitstream leaves the device.
+class VideoWriter {
+ public:
+  VideoWriter(Renderer* gpu, const std::string& path, int width, int height, double fps = 29, int quality = 95)
+      : gpu_(gpu) {
+    if (bh8_sink_open(gpu->ctx_, path.c_str(), width, height, fps, quality, &sink_) != BH8_OK)
+      throw std::runtime_error(std::string("bh8_sink_open: ") + bh8_last_error(gpu->ctx_));
+  }
+  ~VideoWriter() {
+    if (sink_) bh8_sink_close(sink_, nullptr);
+  }
+  VideoWriter(const VideoWriter&) = delete;
+  VideoWriter& operator=(const VideoWriter&) = delete;
+
+  template <typename T>
+  void Write(const ObjectManager<T>& manager, const StaticBlackhole<T>& blackhole, const Camera<T>& camera,
+             int nstep = 20) {
+    const SceneSnapshot snap = Snapshot(manager, blackhole);
+    const bh8_camera cam = Snapshot(camera);
+    gpu_->UploadTextures(snap);
+    const bh8_scene scene = snap.view();
+    bh8_params prm{};
+    prm.nstep = nstep;
+    if (bh8_sink_render(sink_, &scene, &cam, &prm) != BH8_OK)
+      throw std::runtime_error(std::string("bh8_sink_render: ") + bh8_sink_last_error(sink_));
+  }
+
+  // Finishes the file (index, sizes); returns its size in bytes.
+  unsigned long long Release() {
+    uint64_t bytes = 0;
+    bh8_sink* s = sink_;
+    sink_ = nullptr;
+    if (s && bh8_sink_close(s, &bytes) != BH8_OK) throw std::runtime_error("bh8_sink_close: write error");
+    return bytes;
+  }
+
+ private:
+  Renderer* gpu_;
+  bh8_sink* sink_ = nullptr;
 };
 
 }  // namespace gpu

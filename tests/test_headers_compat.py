@@ -91,9 +91,24 @@ def test_gpu_driver_app_matches_reference_frame(textures, tmp_path):
                     "-L" + os.path.join(ROOT, "blackhole_8_b200"), "-lbh8",
                     "-Wl,-rpath," + os.path.join(ROOT, "blackhole_8_b200")], check=True)
     prefix = str(tmp_path / "f")
+    video = str(tmp_path / "video.avi")
     out = subprocess.run([exe, "--cfg", "0", "--width", "960", "--height", "540", "--frames", "8", "--texdir",
-                          textures, "--out", prefix], check=True, capture_output=True, text=True).stdout
+                          textures, "--out", prefix, "--video", video], check=True, capture_output=True,
+                         text=True).stdout
     assert out.count("Took") == 8
+    # the driver's video.avi (blackhole_solution_test.cc:71-72,334), frames encoded on the GPU
+    cv2 = pytest.importorskip("cv2")
+    cap = cv2.VideoCapture(video)
+    frames = []
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        frames.append(fr)
+    assert len(frames) == 8 and frames[0].shape == (540, 960, 3)
+    raw0 = np.fromfile(prefix + "_0.bgr", dtype=np.uint8)[8:].reshape(540, 960, 3)
+    mse = np.mean((frames[0].astype(float) - raw0.astype(float)) ** 2)
+    assert 10 * np.log10(255.0 ** 2 / mse) > 32.0
     g0 = O.load_golden("cfg0_960x540")
     f0 = np.fromfile(prefix + "_0.bgr", dtype=np.uint8)[8:].reshape(540, 960, 3)
     cls_ok = (f0.sum(2) > 0) == (g0["bgr"].sum(2) > 0)

@@ -1,0 +1,147 @@
+"""Frame sink: Motion-JPEG AVI writer behind bh8_sink_*, the stand-in for the reference's
+cv::VideoWriter(fourcc MJPG) of blackhole_solution_test.cc:71-72,334.
+
+A JPEG stream cannot be byte-identical between encoders, so parity here means what a consumer of the
+reference's video.avi relies on: the file is a valid MJPG AVI that OpenCV itself reads back with the
+right frame count, size and rate, and every decoded frame matches the rendered frame as closely as
+OpenCV's own JPEG encoder at the same quality does (PSNR, stated below).
+CPU tests cover the container (fed with JPEGs from cv2.imencode); the `gpu` tests the nvJPEG path."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+
+from blackhole_8_b200 import abi  # noqa: E402
+from blackhole_8_b200.renderer import Bh8Error, VideoSink  # noqa: E402
+
+import oracle_lib as O  # noqa: E402
+
+PSNR_MIN_DB = 34.0          # quality 95, 4:2:0: OpenCV's own encoder + AVI reader give 37-38 dB on these frames
+PSNR_BELOW_OPENCV_DB = 3.0  # nvJPEG may be at most this much worse than cv2.imencode at equal quality
+
+
+def psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else 10.0 * np.log10(255.0 ** 2 / mse)
+
+
+def read_avi(path):
+    cap = cv2.VideoCapture(path)
+    assert cap.isOpened(), "OpenCV cannot open the AVI"
+    info = {"fps": cap.get(cv2.CAP_PROP_FPS), "w": int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)),
+            "h": int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)), "fourcc": int(cap.get(cv2.CAP_PROP_FOURCC))}
+    frames = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        frames.append(f)
+    cap.release()
+    return info, frames
+
+
+def test_container_is_a_valid_mjpg_avi(tmp_path):
+    g = O.load_golden("cfg1_640x360")
+    frame = np.ascontiguousarray(g["bgr"])
+    h, w = frame.shape[:2]
+    path = str(tmp_path / "video.avi")
+    jpegs = []
+    with VideoSink(None, path, w, h, fps=29, quality=95) as sink:
+        for k in range(5):
+            f = np.roll(frame, 7 * k, axis=1)
+            ok, enc = cv2.imencode(".jpg", f, [cv2.IMWRITE_JPEG_QUALITY, 95])
+            assert ok
+            jpegs.append((f, enc.tobytes()))
+            sink.append_jpeg(jpegs[-1][1])
+            assert sink.last_jpeg() == jpegs[-1][1]
+        st = sink.stats()
+        assert st["frames"] == 5 and st["jpeg_bytes"] == sum(len(j) for _, j in jpegs)
+        size = sink.close()
+    assert size == os.path.getsize(path)
+    raw = open(path, "rb").read()
+    # RIFF header, stream handler, frame count in avih and strh, index
+    assert raw[:4] == b"RIFF" and raw[8:12] == b"AVI " and struct.unpack("<I", raw[4:8])[0] == len(raw) - 8
+    assert raw.count(b"00dc") == 10 and b"idx1" in raw and b"vidsMJPG" in raw
+    avih = raw.index(b"avih")
+    assert struct.unpack("<I", raw[avih + 8 + 16:avih + 8 + 20])[0] == 5
+    info, frames = read_avi(path)
+    assert (info["w"], info["h"]) == (w, h) and abs(info["fps"] - 29.0) < 1e-6
+    assert info["fourcc"] == cv2.VideoWriter_fourcc(*"MJPG")
+    assert len(frames) == 5
+    for (src, enc), got in zip(jpegs, frames):
+        ref = cv2.imdecode(np.frombuffer(enc, np.uint8), cv2.IMREAD_COLOR)
+        assert psnr(got, ref) > 40.0        # same bitstream, two decoders (ffmpeg vs libjpeg-turbo colour conversion)
+        assert psnr(got, src) > PSNR_MIN_DB
+
+
+def test_sink_rejects_bad_input(tmp_path):
+    with pytest.raises(Bh8Error):
+        VideoSink(None, str(tmp_path / "no_such_dir" / "v.avi"), 64, 64)
+    with pytest.raises(Bh8Error):
+        VideoSink(None, None, 0, 64)
+    with pytest.raises(Bh8Error):
+        VideoSink(None, None, 64, 64, quality=0)
+    sink = VideoSink(None, None, 64, 64)
+    with pytest.raises(Bh8Error):
+        sink.append_jpeg(b"not a jpeg at all")
+    with pytest.raises(Bh8Error):
+        sink.write_device(0x1000)  # a host-only sink has no encoder
+    sink.close()
+
+
+@pytest.mark.gpu
+def test_gpu_encoded_frames_match_the_rendered_frames(tmp_path):
+    from gpu_util import renderer
+    g = O.load_golden("cfg1_640x360")
+    snap = g["snap"]
+    r = renderer()
+    r.set_textures(snap, O.load_texture)
+    h, w = snap.height, snap.width
+    path = str(tmp_path / "video.avi")
+    rendered = []
+    with VideoSink(r, path, w, h, fps=29, quality=95) as sink:
+        for k in range(6):
+            d = snap.to_dict()
+            d["camera"]["pos"] = [d["camera"]["pos"][0] + 40.0 * k] + list(d["camera"]["pos"][1:])
+            s = abi.SceneSnapshot.from_dict(d)
+            sink.render(s)
+            jpg = sink.last_jpeg()
+            assert jpg[:2] == b"\xff\xd8" and jpg[-2:] == b"\xff\xd9"
+            frame = r.render(s, pixel_format=abi.PIXEL_BGR8)["pixels"][0]
+            rendered.append((frame, jpg))
+        st = sink.stats()
+        assert st["frames"] == 6 and st["encode_ms"] > 0
+        sink.close()
+    info, frames = read_avi(path)
+    assert (info["w"], info["h"]) == (w, h) and len(frames) == 6
+    for (frame, jpg), got in zip(rendered, frames):
+        dec = cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_COLOR)
+        ok, enc = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_QUALITY, 95])
+        ref = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+        p_gpu, p_cv = psnr(dec, frame), psnr(ref, frame)
+        print("PSNR nvJPEG %.2f dB, OpenCV %.2f dB, bytes %d vs %d" % (p_gpu, p_cv, len(jpg), len(enc)))
+        assert p_gpu > PSNR_MIN_DB and p_gpu > p_cv - PSNR_BELOW_OPENCV_DB
+        assert psnr(got, dec) > 40.0
+        assert 0.4 < len(jpg) / len(enc) < 2.5
+
+
+@pytest.mark.gpu
+def test_write_device_takes_a_frame_rendered_elsewhere():
+    from gpu_util import renderer
+    g = O.load_golden("cfg1_odd_333x187")  # odd size: exercises nvJPEG's edge blocks
+    snap = g["snap"]
+    r = renderer()
+    r.set_textures(snap, O.load_texture)
+    h, w = snap.height, snap.width
+    buf = r.frame_alloc(h * w * 3)
+    r.render_device(snap, buf, pixel_format=abi.PIXEL_BGR8)
+    r.sync()
+    sink = VideoSink(r, None, w, h)
+    sink.write_device(buf)
+    dec = cv2.imdecode(np.frombuffer(sink.last_jpeg(), np.uint8), cv2.IMREAD_COLOR)
+    sink.close()
+    assert dec.shape == (h, w, 3)
+    assert psnr(dec, np.ascontiguousarray(g["bgr"])) > PSNR_MIN_DB - 4.0  # small, busy frame
