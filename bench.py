@@ -310,47 +310,68 @@ def bench_8k_stripes(args, r, base, rank, world, flags):
     }))
 
 
-def measure_sink(r, seq, W, H, frames=120, quality=95):
+def measure_sink(r, my_frames, W, H, world=1, rank=0, frames=120, quality=95):
     """SURVEY 8f-2, reported beside the headline: frames/s of the GPU frame sink (bh8_sink_render: trace the
     frame, JPEG-encode it on the device with nvJPEG, only the bitstream comes to the host) -- what the
     reference's `out_capture.write(frame)` becomes -- next to OpenCV's own JPEG encoder on one host core,
-    which is what cv::VideoWriter(MJPG) spends per frame.  Not part of value / e2e."""
+    which is what cv::VideoWriter(MJPG) spends per frame.  One sink per rank / GPU on that rank's frames;
+    whole-job rate = world * frames / (max over ranks of the wall time).  Not part of value / e2e."""
+    import torch
+    import torch.distributed as dist
+    err, out = None, {}
     try:
         import cv2
         from blackhole_8_b200 import abi
         from blackhole_8_b200.renderer import VideoSink
         sink = VideoSink(r, None, W, H, fps=29, quality=quality)
         for i in range(5):
-            sink.render(seq[i % len(seq)])
+            sink.render(my_frames[i % len(my_frames)])
         before = sink.stats()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for i in range(frames):
-            sink.render(seq[i % len(seq)])
+            sink.render(my_frames[i % len(my_frames)])
         dt = time.perf_counter() - t0
         st = sink.stats()
         jpg = sink.last_jpeg()
         sink.close()
-        frame = r.render(seq[(frames - 1) % len(seq)], pixel_format=abi.PIXEL_BGR8)["pixels"][0]
-        dec = cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_COLOR)
-        mse = float(np.mean((dec.astype(np.float64) - frame.astype(np.float64)) ** 2))
-        n_cpu = 8
-        t0 = time.perf_counter()
-        for _ in range(n_cpu):
-            ok, enc = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_QUALITY, quality])
-        cpu_dt = time.perf_counter() - t0
-        ref = cv2.imdecode(enc, cv2.IMREAD_COLOR)
-        mse_cpu = float(np.mean((ref.astype(np.float64) - frame.astype(np.float64)) ** 2))
         n = st["frames"] - before["frames"]
-        return {"what": "bh8_sink_render: render + nvJPEG encode (4:2:0, quality %d) on the GPU, bitstream to host" % quality,
-                "frames_per_s": n / dt, "Mrays_per_s": n * W * H / dt / 1e6,
-                "jpeg_bytes_per_frame": (st["jpeg_bytes"] - before["jpeg_bytes"]) / n,
-                "raw_bytes_per_frame": W * H * 3,
-                "nvjpeg_device_ms_per_frame": (st["encode_ms"] - before["encode_ms"]) / n,
-                "psnr_db": 10.0 * np.log10(255.0 ** 2 / mse) if mse > 0 else 99.0,
-                "host_opencv_imencode": {"frames_per_s": n_cpu / cpu_dt, "cores": 1, "bytes_per_frame": len(enc),
-                                         "psnr_db": 10.0 * np.log10(255.0 ** 2 / mse_cpu) if mse_cpu > 0 else 99.0}}
+        out = {"dt": dt, "n": n, "jpeg_bytes": st["jpeg_bytes"] - before["jpeg_bytes"],
+               "encode_ms": st["encode_ms"] - before["encode_ms"]}
+        if rank == 0:
+            frame = r.render(my_frames[(frames - 1) % len(my_frames)], pixel_format=abi.PIXEL_BGR8)["pixels"][0]
+            dec = cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_COLOR)
+            mse = float(np.mean((dec.astype(np.float64) - frame.astype(np.float64)) ** 2))
+            n_cpu = 8
+            t0 = time.perf_counter()
+            for _ in range(n_cpu):
+                ok, enc = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_QUALITY, quality])
+            cpu_dt = time.perf_counter() - t0
+            ref = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+            mse_cpu = float(np.mean((ref.astype(np.float64) - frame.astype(np.float64)) ** 2))
+            out.update(psnr=10.0 * np.log10(255.0 ** 2 / mse) if mse > 0 else 99.0,
+                       cpu={"frames_per_s": n_cpu / cpu_dt, "cores": 1, "bytes_per_frame": len(enc),
+                            "psnr_db": 10.0 * np.log10(255.0 ** 2 / mse_cpu) if mse_cpu > 0 else 99.0})
     except Exception as e:  # the sink is an extra: never fail the headline line over it
-        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        err = "%s: %s" % (type(e).__name__, e)
+    dt_max = out.get("dt", 0.0)
+    ok_all = 0.0 if err else 1.0
+    if world > 1:  # every rank takes part, also after a failure
+        t = torch.tensor([dt_max, -ok_all], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_max, ok_all = float(t[0].item()), -float(t[1].item())
+    if rank != 0:
+        return None
+    if err or ok_all < 1.0:
+        return {"unavailable": err or "a rank failed"}
+    n = out["n"]
+    return {"what": "bh8_sink_render: render + nvJPEG encode (4:2:0, quality %d) on the GPU, bitstream to host; "
+                    "one sink per GPU" % quality,
+            "frames_per_s": world * n / dt_max, "Mrays_per_s": world * n * W * H / dt_max / 1e6,
+            "jpeg_bytes_per_frame": out["jpeg_bytes"] / n, "raw_bytes_per_frame": W * H * 3,
+            "nvjpeg_device_ms_per_frame": out["encode_ms"] / n, "psnr_db": out["psnr"],
+            "host_opencv_imencode": out["cpu"]}
 
 
 def main():
@@ -528,13 +549,13 @@ def main():
     e2e_sync_value = rays * world * e2e_steps / sync_s / 1e6
     frame_ok = bool(pinned[0].array[0, :, :, 3].min() == 255 and pinned[1].array[0, :, :, 3].min() == 255)
 
+    sink = measure_sink(r, my_frames, W, H, world, rank)  # every rank: one sink per GPU
+
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
-
-    sink = measure_sink(r, seq, W, H) if world == 1 else None
 
     # ---- roofline: algorithmic FP64 flops / kernel time vs the DFMA peak measured now ----------
     n_extra = max(0, base.scene.n_obj - 2)
