@@ -147,6 +147,10 @@ extern "C" int bh8_harness_solve(double mass, const double* b, int n, double* fa
   return 0;
 }
 
+extern "C" void bh8_harness_atan2f(const float* y, const float* x, int n, float* out) {
+  for (int i = 0; i < n; ++i) out[i] = bh8::fast_atan2f(y[i], x[i]);
+}
+
 extern "C" void bh8_harness_sincos(const double* x, int n, double* s, double* c) {
   for (int i = 0; i < n; ++i) bh8::sincos_(x[i], &s[i], &c[i]);
 }

@@ -120,6 +120,24 @@ def test_sincos_primitive_is_within_one_ulp():
     assert np.abs(c - np.cos(x)).max() <= 2.3e-16
 
 
+def test_fast_atan2f_error_is_inside_the_arming_margin():
+    """arm_central's FP32 atan2 must stay well inside kArmMargin (8e-6 rad)."""
+    L = harness()
+    rng = np.random.default_rng(11)
+    ang = np.concatenate([rng.random(2_000_000) * 2 * np.pi - np.pi,
+                          np.arange(-8, 9) * (np.pi / 8), np.arange(-8, 9) * (np.pi / 8) + 1e-6])
+    rad = 10.0 ** (rng.random(len(ang)) * 12 - 6)
+    x = (rad * np.cos(ang)).astype(np.float32)
+    y = (rad * np.sin(ang)).astype(np.float32)
+    out = np.empty(len(ang), np.float32)
+    L.bh8_harness_atan2f(y.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), C.c_int(len(ang)),
+                         out.ctypes.data_as(C.c_void_p))
+    ref = np.arctan2(y.astype(np.float64), x.astype(np.float64))
+    err = np.abs(out.astype(np.float64) - ref)
+    err = np.minimum(err, 2 * np.pi - err)  # +pi and -pi are the same direction
+    assert err.max() < 1e-6, err.max()
+
+
 @pytest.mark.parametrize("name", ["cfg1_640x360", "cfg2_640x360", "cfg9_inside_320x180", "cfg6_offplane_400x225"])
 def test_frozen_lanes_are_inert(name):
     """The kernel's warps run the straight-line update for every lane, frozen (parked / ended) ones
