@@ -24,6 +24,10 @@ struct Device {
   int ordinal = 0;
   cudaStream_t stream = nullptr;       // kernels
   cudaStream_t copy_stream = nullptr;  // D2H of finished frames
+  // bh8_submit: one stream per staging slot carries a frame's kernel AND its read-back, so the
+  // kernel of frame k+1 (other slot, other stream) starts on the SMs frame k's last wave leaves idle
+  // and runs under frame k's copy.
+  cudaStream_t slot_stream[2] = {nullptr, nullptr};
   cudaArray_t tex_array[BH8_MAX_TEXTURES] = {};
   cudaTextureObject_t tex_obj[BH8_MAX_TEXTURES] = {};
   unsigned long long* d_stats = nullptr;  // 8 counters
@@ -50,6 +54,7 @@ struct bh8_ctx {
   std::string err;
   uint64_t launches = 0;
   uint64_t next_ticket = 0;  // bh8_submit
+  bool submit_slot_streams = true;  // $BH8_SUBMIT_ONE_STREAM=1: kernels on one stream, copies on another (A/B knob)
   std::vector<void*> owned;  // bh8_frame_alloc results (device 0)
 };
 
@@ -92,7 +97,8 @@ int make_grid(const Bh8Frame& f, dim3* grid) {
 }
 
 int launch_frame(bh8_ctx* ctx, Device& d, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
-                 void* d_pixels, void* d_cls, void* d_key, void* d_steps) {
+                 void* d_pixels, void* d_cls, void* d_key, void* d_steps, cudaStream_t st = nullptr) {
+  if (!st) st = d.stream;
   Bh8Frame f;
   char msg[192];
   const int rc = bh8_build_frame(scene, cam, prm, ctx->tex_rows, ctx->tex_cols, &f, msg);
@@ -118,18 +124,18 @@ int launch_frame(bh8_ctx* ctx, Device& d, const bh8_scene* scene, const bh8_came
   // One instantiation per number of non-central planes with an FP32 side filter; scenes with more
   // planes than filter slots take the generic instantiation (exact test on every gated step).
   if (f.tracer == BH8_TRACER_LINEAR) {
-    bh8::bh8_linear_kernel<<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out);
+    bh8::bh8_linear_kernel<<<grid, bh8::kThreads, 0, st>>>(f, tex, out);
     BH8_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return BH8_OK;
   }
   switch (f.n_nc <= bh8::kMaxFilterPlanes ? f.n_nc : -1) {
-    case 0: bh8::bh8_render_kernel<0><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
-    case 1: bh8::bh8_render_kernel<1><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
-    case 2: bh8::bh8_render_kernel<2><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
-    case 3: bh8::bh8_render_kernel<3><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
-    case 4: bh8::bh8_render_kernel<4><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
-    default: bh8::bh8_render_kernel<-1><<<grid, bh8::kThreads, 0, d.stream>>>(f, tex, out); break;
+    case 0: bh8::bh8_render_kernel<0><<<grid, bh8::kThreads, 0, st>>>(f, tex, out); break;
+    case 1: bh8::bh8_render_kernel<1><<<grid, bh8::kThreads, 0, st>>>(f, tex, out); break;
+    case 2: bh8::bh8_render_kernel<2><<<grid, bh8::kThreads, 0, st>>>(f, tex, out); break;
+    case 3: bh8::bh8_render_kernel<3><<<grid, bh8::kThreads, 0, st>>>(f, tex, out); break;
+    case 4: bh8::bh8_render_kernel<4><<<grid, bh8::kThreads, 0, st>>>(f, tex, out); break;
+    default: bh8::bh8_render_kernel<-1><<<grid, bh8::kThreads, 0, st>>>(f, tex, out); break;
   }
   BH8_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
@@ -202,6 +208,7 @@ int bh8_create(bh8_ctx** out, const int* devices, int n_dev) {
   bh8_ctx* ctx = new (std::nothrow) bh8_ctx();
   if (!ctx) return fail(nullptr, BH8_ENOMEM, "out of host memory");
   ctx->n_dev = n_dev;
+  if (const char* one = std::getenv("BH8_SUBMIT_ONE_STREAM")) ctx->submit_slot_streams = std::atoi(one) == 0;
   for (int i = 0; i < n_dev; ++i) {
     Device& d = ctx->dev[i];
     d.ordinal = devices ? devices[i] : i;
@@ -230,6 +237,7 @@ int bh8_create(bh8_ctx** out, const int* devices, int n_dev) {
     }
     BH8_CREATE_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     BH8_CREATE_CUDA(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) BH8_CREATE_CUDA(cudaStreamCreateWithFlags(&d.slot_stream[b], cudaStreamNonBlocking));
     BH8_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.d_stats), 8 * sizeof(unsigned long long)));
     BH8_CREATE_CUDA(cudaMemset(d.d_stats, 0, 8 * sizeof(unsigned long long)));
     for (int b = 0; b < 2; ++b) {
@@ -281,6 +289,8 @@ void bh8_destroy(bh8_ctx* ctx) {
       for (void* p : ctx->owned) cudaFree(p);
     if (d.stream) cudaStreamDestroy(d.stream);
     if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+    for (int b = 0; b < 2; ++b)
+      if (d.slot_stream[b]) cudaStreamDestroy(d.slot_stream[b]);
   }
   delete ctx;
 }
@@ -344,6 +354,7 @@ int bh8_sync(bh8_ctx* ctx) {
     BH8_CUDA(ctx, cudaSetDevice(ctx->dev[i].ordinal));
     BH8_CUDA(ctx, cudaStreamSynchronize(ctx->dev[i].stream));
     BH8_CUDA(ctx, cudaStreamSynchronize(ctx->dev[i].copy_stream));
+    for (int b = 0; b < 2; ++b) BH8_CUDA(ctx, cudaStreamSynchronize(ctx->dev[i].slot_stream[b]));
   }
   return BH8_OK;
 }
@@ -516,13 +527,16 @@ int bh8_submit(bh8_ctx* ctx, const bh8_scene* scene, const bh8_camera* cam, cons
   bh8_params p = *params;
   p.shard_count = 0;
   p.shard_index = 0;
-  const int rc = launch_frame(ctx, d, scene, cam, &p, d.d_pix[b], nullptr, nullptr, nullptr);
+  cudaStream_t st = ctx->submit_slot_streams ? d.slot_stream[b] : d.stream;
+  const int rc = launch_frame(ctx, d, scene, cam, &p, d.d_pix[b], nullptr, nullptr, nullptr, st);
   if (rc != BH8_OK) return rc;
-  BH8_CUDA(ctx, cudaEventRecord(d.ev_kernel_done[b], d.stream));
-  BH8_CUDA(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_kernel_done[b], 0));
-  BH8_CUDA(ctx, cudaMemcpyAsync(out_pixels, d.d_pix[b], npx * bh8_pixel_bytes(p.pixel_format), cudaMemcpyDeviceToHost,
-                                d.copy_stream));
-  BH8_CUDA(ctx, cudaEventRecord(d.ev_copy_done[b], d.copy_stream));
+  if (!ctx->submit_slot_streams) {
+    BH8_CUDA(ctx, cudaEventRecord(d.ev_kernel_done[b], st));
+    st = d.copy_stream;
+    BH8_CUDA(ctx, cudaStreamWaitEvent(st, d.ev_kernel_done[b], 0));
+  }
+  BH8_CUDA(ctx, cudaMemcpyAsync(out_pixels, d.d_pix[b], npx * bh8_pixel_bytes(p.pixel_format), cudaMemcpyDeviceToHost, st));
+  BH8_CUDA(ctx, cudaEventRecord(d.ev_copy_done[b], st));
   d.slot_busy[b] = true;
   *ticket = t;
   ctx->next_ticket = t + 1;
