@@ -335,9 +335,20 @@ def measure_sink(r, my_frames, W, H, world=1, rank=0, frames=120, quality=95):
         dt = time.perf_counter() - t0
         st = sink.stats()
         jpg = sink.last_jpeg()
+        # pipelined form (bh8_sink_submit): frame k+1 is traced while frame k is encoded / read back
+        for i in range(5):
+            sink.submit(my_frames[i % len(my_frames)])
+        sink.flush()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(frames):
+            sink.submit(my_frames[i % len(my_frames)])
+        sink.flush()
+        dt_pipe = time.perf_counter() - t0
         sink.close()
         n = st["frames"] - before["frames"]
-        out = {"dt": dt, "n": n, "jpeg_bytes": st["jpeg_bytes"] - before["jpeg_bytes"],
+        out = {"dt": dt, "dt_pipe": dt_pipe, "n": n, "jpeg_bytes": st["jpeg_bytes"] - before["jpeg_bytes"],
                "encode_ms": st["encode_ms"] - before["encode_ms"]}
         if rank == 0:
             frame = r.render(my_frames[(frames - 1) % len(my_frames)], pixel_format=abi.PIXEL_BGR8)["pixels"][0]
@@ -355,12 +366,12 @@ def measure_sink(r, my_frames, W, H, world=1, rank=0, frames=120, quality=95):
                             "psnr_db": 10.0 * np.log10(255.0 ** 2 / mse_cpu) if mse_cpu > 0 else 99.0})
     except Exception as e:  # the sink is an extra: never fail the headline line over it
         err = "%s: %s" % (type(e).__name__, e)
-    dt_max = out.get("dt", 0.0)
+    dt_max, dt_pipe_max = out.get("dt", 0.0), out.get("dt_pipe", 0.0)
     ok_all = 0.0 if err else 1.0
     if world > 1:  # every rank takes part, also after a failure
-        t = torch.tensor([dt_max, -ok_all], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dt_max, -ok_all, dt_pipe_max], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_max, ok_all = float(t[0].item()), -float(t[1].item())
+        dt_max, ok_all, dt_pipe_max = float(t[0].item()), -float(t[1].item()), float(t[2].item())
     if rank != 0:
         return None
     if err or ok_all < 1.0:
@@ -369,6 +380,9 @@ def measure_sink(r, my_frames, W, H, world=1, rank=0, frames=120, quality=95):
     return {"what": "bh8_sink_render: render + nvJPEG encode (4:2:0, quality %d) on the GPU, bitstream to host; "
                     "one sink per GPU" % quality,
             "frames_per_s": world * n / dt_max, "Mrays_per_s": world * n * W * H / dt_max / 1e6,
+            "pipelined_bh8_sink_submit": {"frames_per_s": world * n / dt_pipe_max,
+                                          "Mrays_per_s": world * n * W * H / dt_pipe_max / 1e6,
+                                          "what": "two frames in flight: frame k+1 traced while frame k is encoded"},
             "jpeg_bytes_per_frame": out["jpeg_bytes"] / n, "raw_bytes_per_frame": W * H * 3,
             "nvjpeg_device_ms_per_frame": out["encode_ms"] / n, "psnr_db": out["psnr"],
             "host_opencv_imencode": out["cpu"]}

@@ -8,7 +8,7 @@ import json
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_OBJECTS = 16
 MAX_TEXTURES = 16
 

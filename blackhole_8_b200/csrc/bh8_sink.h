@@ -14,6 +14,7 @@
 #include <nvjpeg.h>
 
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -142,6 +143,97 @@ class AviMjpgWriter {
   std::vector<Entry> index_;
 };
 
+// Reader for the files AviMjpgWriter produces (and any AVI 1.0 whose video chunks are '00dc' / '00db'
+// inside LIST 'movi'): frame sizes and offsets from a walk over the chunk tree.
+class AviMjpgReader {
+ public:
+  struct Frame {
+    long offset;
+    uint32_t size;
+  };
+  bool open(const char* path, std::string* err) {
+    fp_ = std::fopen(path, "rb");
+    if (!fp_) {
+      *err = std::string("cannot open ") + path;
+      return false;
+    }
+    char id[4];
+    uint32_t size = 0;
+    if (!tag(id) || std::memcmp(id, "RIFF", 4) != 0 || !u32(&size) || !tag(id) || std::memcmp(id, "AVI ", 4) != 0) {
+      *err = std::string(path) + " is not a RIFF AVI file";
+      return false;
+    }
+    std::fseek(fp_, 0, SEEK_END);
+    const long file_end = std::ftell(fp_);
+    if (!walk(12, file_end, err)) return false;
+    if (width_ <= 0 || height_ <= 0 || !(fps_ > 0)) {
+      *err = std::string(path) + ": no avih / strh header found";
+      return false;
+    }
+    return true;
+  }
+  bool read(size_t k, std::vector<uint8_t>* out, std::string* err) {
+    out->resize(frames_[k].size);
+    std::fseek(fp_, frames_[k].offset, SEEK_SET);
+    if (std::fread(out->data(), 1, out->size(), fp_) != out->size()) {
+      *err = "short read on an AVI part";
+      return false;
+    }
+    return true;
+  }
+  size_t frames() const { return frames_.size(); }
+  int width() const { return width_; }
+  int height() const { return height_; }
+  double fps() const { return fps_; }
+  ~AviMjpgReader() {
+    if (fp_) std::fclose(fp_);
+  }
+
+ private:
+  bool tag(char* id) { return std::fread(id, 1, 4, fp_) == 4; }
+  bool u32(uint32_t* v) {
+    uint8_t b[4];
+    if (std::fread(b, 1, 4, fp_) != 4) return false;
+    *v = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+    return true;
+  }
+  bool walk(long at, long end, std::string* err) {
+    while (at + 8 <= end) {
+      std::fseek(fp_, at, SEEK_SET);
+      char id[4];
+      uint32_t size = 0;
+      if (!tag(id) || !u32(&size)) break;
+      const long body = at + 8;
+      if (body + (long)size > end) {
+        *err = "truncated chunk in an AVI part";
+        return false;
+      }
+      if (std::memcmp(id, "LIST", 4) == 0) {
+        char kind[4];
+        if (!tag(kind)) break;
+        if (!walk(body + 4, body + (long)size, err)) return false;
+      } else if (std::memcmp(id, "avih", 4) == 0 && size >= 40) {
+        uint32_t v[10];
+        for (int i = 0; i < 10; ++i) u32(&v[i]);
+        width_ = (int)v[8];
+        height_ = (int)v[9];
+      } else if (std::memcmp(id, "strh", 4) == 0 && size >= 28) {
+        uint32_t v[7];
+        for (int i = 0; i < 7; ++i) u32(&v[i]);
+        if (v[5]) fps_ = (double)v[6] / (double)v[5];  // dwRate / dwScale
+      } else if (id[0] == '0' && id[1] == '0' && id[2] == 'd' && (id[3] == 'c' || id[3] == 'b')) {
+        frames_.push_back({body, size});
+      }
+      at = body + (long)size + (size & 1);
+    }
+    return true;
+  }
+  FILE* fp_ = nullptr;
+  int width_ = 0, height_ = 0;
+  double fps_ = 0;
+  std::vector<Frame> frames_;
+};
+
 const char* nvjpeg_status_name(nvjpegStatus_t s) {
   switch (s) {
     case NVJPEG_STATUS_SUCCESS: return "success";
@@ -173,6 +265,16 @@ struct bh8_sink {
   nvjpegEncoderParams_t params = nullptr;
   void* d_frame = nullptr;  // BGR8 staging frame for bh8_sink_render
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // bh8_sink_submit: two frames in flight, each with its own stream, staging frame and encoder
+  // state -- the kernel of frame k+1 runs while frame k is being encoded and its bitstream read back.
+  struct Slot {
+    nvjpegEncoderState_t state = nullptr;
+    void* d_frame = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool busy = false;
+  } slot[2];
+  uint64_t submitted = 0;
 };
 
 namespace {
@@ -239,6 +341,33 @@ int sink_commit(bh8_sink* s) {
   return BH8_OK;
 }
 
+// Fetch the bitstream of the frame in flight on this slot and append it to the file.
+int sink_drain(bh8_sink* s, bh8_sink::Slot& sl) {
+  if (!sl.busy) return BH8_OK;
+  sl.busy = false;
+  BH8_SINK_CUDA(s, cudaSetDevice(s->ctx->dev[0].ordinal));
+  size_t length = 0;
+  BH8_NVJPEG(s, nvjpegEncodeRetrieveBitstream(s->handle, sl.state, nullptr, &length, sl.stream));
+  s->jpeg.resize(length);
+  BH8_NVJPEG(s, nvjpegEncodeRetrieveBitstream(s->handle, sl.state, s->jpeg.data(), &length, sl.stream));
+  BH8_SINK_CUDA(s, cudaStreamSynchronize(sl.stream));
+  s->jpeg.resize(length);
+  float ms = 0;
+  BH8_SINK_CUDA(s, cudaEventElapsedTime(&ms, sl.ev0, sl.ev1));
+  s->encode_ms += ms;
+  return sink_commit(s);
+}
+
+// Oldest frame first: frames reach the file in the order they were submitted.
+int sink_flush(bh8_sink* s) {
+  if (!s->ctx) return BH8_OK;
+  for (int k = 0; k < 2; ++k) {
+    const int rc = sink_drain(s, s->slot[(s->submitted + k) & 1]);
+    if (rc != BH8_OK) return rc;
+  }
+  return BH8_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -274,6 +403,8 @@ int bh8_sink_open(bh8_ctx* ctx, const char* avi_path, int width, int height, dou
 int bh8_sink_write_device(bh8_sink* s, const void* d_bgr_frame) {
   if (!s || !d_bgr_frame) return BH8_EINVAL;
   if (!s->ctx) return sink_fail(s, BH8_EINVAL, "this sink was opened without a context: it only takes ready JPEGs");
+  const int rcf = sink_flush(s);
+  if (rcf != BH8_OK) return rcf;
   const int rc = sink_encode(s, d_bgr_frame);
   return rc != BH8_OK ? rc : sink_commit(s);
 }
@@ -284,6 +415,8 @@ int bh8_sink_render(bh8_sink* s, const bh8_scene* scene, const bh8_camera* cam, 
   if (cam->width != s->width || cam->height != s->height)
     return sink_fail(s, BH8_EINVAL, "camera size differs from the sink's frame size");
   Device& d = s->ctx->dev[0];
+  const int rcf = sink_flush(s);
+  if (rcf != BH8_OK) return rcf;
   if (!s->d_frame) {
     BH8_SINK_CUDA(s, cudaSetDevice(d.ordinal));
     BH8_SINK_CUDA(s, cudaMalloc(&s->d_frame, static_cast<size_t>(s->width) * s->height * 3));
@@ -297,9 +430,83 @@ int bh8_sink_render(bh8_sink* s, const bh8_scene* scene, const bh8_camera* cam, 
   return rc2 != BH8_OK ? rc2 : sink_commit(s);
 }
 
+int bh8_sink_submit(bh8_sink* s, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* params) {
+  if (!s || !scene || !cam) return BH8_EINVAL;
+  if (!s->ctx) return sink_fail(s, BH8_EINVAL, "this sink was opened without a context");
+  if (cam->width != s->width || cam->height != s->height)
+    return sink_fail(s, BH8_EINVAL, "camera size differs from the sink's frame size");
+  Device& d = s->ctx->dev[0];
+  bh8_sink::Slot& sl = s->slot[s->submitted & 1];
+  const int rcd = sink_drain(s, sl);  // the frame submitted two calls ago
+  if (rcd != BH8_OK) return rcd;
+  BH8_SINK_CUDA(s, cudaSetDevice(d.ordinal));
+  if (!sl.stream) {
+    BH8_SINK_CUDA(s, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    BH8_SINK_CUDA(s, cudaEventCreate(&sl.ev0));
+    BH8_SINK_CUDA(s, cudaEventCreate(&sl.ev1));
+    BH8_NVJPEG(s, nvjpegEncoderStateCreate(s->handle, &sl.state, sl.stream));
+    BH8_SINK_CUDA(s, cudaMalloc(&sl.d_frame, static_cast<size_t>(s->width) * s->height * 3));
+  }
+  bh8_params prm{};
+  if (params) prm = *params;
+  prm.pixel_format = BH8_PIXEL_BGR8;
+  const int rc = launch_frame(s->ctx, d, scene, cam, &prm, sl.d_frame, nullptr, nullptr, nullptr, sl.stream);
+  if (rc != BH8_OK) return sink_fail(s, rc, s->ctx->err);
+  nvjpegImage_t img{};
+  img.channel[0] = static_cast<unsigned char*>(sl.d_frame);
+  img.pitch[0] = static_cast<size_t>(s->width) * 3;
+  BH8_SINK_CUDA(s, cudaEventRecord(sl.ev0, sl.stream));
+  BH8_NVJPEG(s, nvjpegEncodeImage(s->handle, sl.state, s->params, &img, NVJPEG_INPUT_BGRI, s->width, s->height,
+                                  sl.stream));
+  BH8_SINK_CUDA(s, cudaEventRecord(sl.ev1, sl.stream));
+  sl.busy = true;
+  s->submitted++;
+  return BH8_OK;
+}
+
+int bh8_sink_flush(bh8_sink* s) {
+  if (!s) return BH8_EINVAL;
+  return sink_flush(s);
+}
+
+int bh8_sink_merge(const char* const* part_paths, int n_parts, const char* out_path, uint64_t* frames,
+                   uint64_t* file_bytes) {
+  if (frames) *frames = 0;
+  if (file_bytes) *file_bytes = 0;
+  if (!part_paths || n_parts < 1 || n_parts > 1024 || !out_path)
+    return fail(nullptr, BH8_EINVAL, "bh8_sink_merge: bad arguments");
+  std::vector<AviMjpgReader> parts(n_parts);
+  std::string err;
+  uint64_t total = 0;
+  for (int i = 0; i < n_parts; ++i) {
+    if (!part_paths[i] || !parts[i].open(part_paths[i], &err)) return fail(nullptr, BH8_EINVAL, "bh8_sink_merge: " + err);
+    if (parts[i].width() != parts[0].width() || parts[i].height() != parts[0].height() ||
+        parts[i].fps() != parts[0].fps())
+      return fail(nullptr, BH8_EINVAL, "bh8_sink_merge: the parts differ in frame size or rate");
+    total += parts[i].frames();
+  }
+  // frame k of the job is frame k / n of part k % n (sharding.frames_of: whole frames round-robin)
+  for (int i = 0; i < n_parts; ++i)
+    if (parts[i].frames() != (total + n_parts - 1 - i) / n_parts)
+      return fail(nullptr, BH8_EINVAL, "bh8_sink_merge: frame counts of the parts are not a round-robin split");
+  AviMjpgWriter out;
+  if (!out.open(out_path, parts[0].width(), parts[0].height(), parts[0].fps(), &err))
+    return fail(nullptr, BH8_EINVAL, "bh8_sink_merge: " + err);
+  std::vector<uint8_t> buf;
+  for (uint64_t k = 0; k < total; ++k) {
+    if (!parts[k % n_parts].read(k / n_parts, &buf, &err) || !out.append(buf.data(), buf.size(), &err))
+      return fail(nullptr, BH8_EINVAL, "bh8_sink_merge: " + err);
+  }
+  if (!out.close(file_bytes, &err)) return fail(nullptr, BH8_EINVAL, "bh8_sink_merge: " + err);
+  if (frames) *frames = total;
+  return BH8_OK;
+}
+
 int bh8_sink_append_jpeg(bh8_sink* s, const uint8_t* jpeg, size_t bytes) {
   if (!s || !jpeg || bytes < 4) return BH8_EINVAL;
   if (jpeg[0] != 0xFF || jpeg[1] != 0xD8) return sink_fail(s, BH8_EINVAL, "not a JPEG stream (no SOI marker)");
+  const int rcf = sink_flush(s);
+  if (rcf != BH8_OK) return rcf;
   s->jpeg.assign(jpeg, jpeg + bytes);
   return sink_commit(s);
 }
@@ -324,10 +531,18 @@ const char* bh8_sink_last_error(const bh8_sink* s) { return s ? s->err.c_str() :
 int bh8_sink_close(bh8_sink* s, uint64_t* file_bytes) {
   if (!s) return BH8_EINVAL;
   if (file_bytes) *file_bytes = 0;
-  int rc = BH8_OK;
+  int rc = sink_flush(s);  // frames still in flight belong to the file
   if (s->avi.is_open() && !s->avi.close(file_bytes, &s->err)) rc = BH8_EINVAL;
   if (s->ctx) {
     cudaSetDevice(s->ctx->dev[0].ordinal);
+    for (bh8_sink::Slot& sl : s->slot) {
+      if (sl.stream) cudaStreamSynchronize(sl.stream);
+      if (sl.state) nvjpegEncoderStateDestroy(sl.state);
+      if (sl.d_frame) cudaFree(sl.d_frame);
+      if (sl.ev0) cudaEventDestroy(sl.ev0);
+      if (sl.ev1) cudaEventDestroy(sl.ev1);
+      if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     if (s->params) nvjpegEncoderParamsDestroy(s->params);
     if (s->state) nvjpegEncoderStateDestroy(s->state);
     if (s->handle) nvjpegDestroy(s->handle);

@@ -66,6 +66,9 @@ def load_library(path=None):
         "bh8_measure_stepping": (i32, [vp, i32, C.POINTER(C.c_double)]),
         "bh8_sink_open": (i32, [vp, C.c_char_p, i32, i32, C.c_double, i32, C.POINTER(vp)]),
         "bh8_sink_render": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params)]),
+        "bh8_sink_submit": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params)]),
+        "bh8_sink_flush": (i32, [vp]),
+        "bh8_sink_merge": (i32, [C.POINTER(C.c_char_p), i32, C.c_char_p, C.POINTER(u64), C.POINTER(u64)]),
         "bh8_sink_write_device": (i32, [vp, vp]),
         "bh8_sink_append_jpeg": (i32, [vp, vp, C.c_size_t]),
         "bh8_sink_last_jpeg": (i32, [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
@@ -292,6 +295,15 @@ class VideoSink:
         prm = snap.params(abi.PIXEL_BGR8, flags, nstep)
         self._check(self.lib.bh8_sink_render(self._h, C.byref(snap.scene), C.byref(snap.camera), C.byref(prm)))
 
+    def submit(self, snap, nstep=None, flags=0):
+        """Pipelined render(): returns once the frame's kernel and encode are queued; frame k+1 is
+        traced while frame k is encoded.  flush() / close() append what is still in flight."""
+        prm = snap.params(abi.PIXEL_BGR8, flags, nstep)
+        self._check(self.lib.bh8_sink_submit(self._h, C.byref(snap.scene), C.byref(snap.camera), C.byref(prm)))
+
+    def flush(self):
+        self._check(self.lib.bh8_sink_flush(self._h))
+
     def write_device(self, d_bgr_frame):
         self._check(self.lib.bh8_sink_write_device(self._h, C.c_void_p(d_bgr_frame)))
 
@@ -325,3 +337,15 @@ class VideoSink:
 
     def __exit__(self, *exc):
         self.close()
+
+
+def merge_video_parts(part_paths, out_path):
+    """One MJPG AVI from the per-GPU files of a frame-sharded job (bh8_sink_merge): frame k of the result
+    is frame k // n of part k % n.  Host only.  Returns (frames, file_bytes)."""
+    lib = load_library()
+    arr = (C.c_char_p * len(part_paths))(*[p.encode() for p in part_paths])
+    frames, size = C.c_uint64(), C.c_uint64()
+    rc = lib.bh8_sink_merge(arr, len(part_paths), out_path.encode(), C.byref(frames), C.byref(size))
+    if rc != 0:
+        raise Bh8Error(rc, (lib.bh8_last_error(None) or b"").decode())
+    return frames.value, size.value

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BH8_ABI_VERSION 3
+#define BH8_ABI_VERSION 4
 #define BH8_MAX_OBJECTS 16
 #define BH8_MAX_TEXTURES 16
 #define BH8_MAX_DEVICES 8
@@ -168,7 +168,8 @@ int bh8_render(bh8_ctx* ctx, const bh8_scene* scenes, const bh8_camera* cams, in
 /* Streaming form of bh8_render for one frame at a time: bh8_submit() launches the frame and queues
  * its read-back into out_pixels (HOST memory, ideally from bh8_host_alloc) and returns at once with
  * a ticket; bh8_wait() blocks until that frame is complete in out_pixels.  Two frames per device
- * may be in flight, so the copy of frame k overlaps the kernel of frame k+1; frames go to the
+ * may be in flight, each on its own stream (kernel, then read-back): the kernel of frame k+1 takes
+ * the SMs frame k's last wave leaves idle and runs under frame k's copy; frames go to the
  * context's devices round-robin.  Tickets must be waited for in order of submission. */
 int bh8_submit(bh8_ctx* ctx, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* params,
                uint8_t* out_pixels, uint64_t* ticket);
@@ -229,6 +230,13 @@ int bh8_sink_open(bh8_ctx* ctx, const char* avi_path, int width, int height, dou
 /* Render one frame (as bh8_render_device, pixel format forced to BGR8) into the sink's own device
  * buffer, encode it and append it: the GPU form of "trace the frame; out_capture.write(frame)". */
 int bh8_sink_render(bh8_sink* sink, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* params);
+/* Pipelined form of bh8_sink_render: queues the frame's kernel and its JPEG encode on one of two
+ * internal streams and returns; the bitstream is fetched and appended when the slot is needed again
+ * (two calls later), by bh8_sink_flush() or by bh8_sink_close().  Frame k+1 is traced while frame k
+ * is encoded and read back; frames reach the file in submission order.  bh8_sink_last_jpeg() and
+ * bh8_sink_stats() describe the frames appended so far. */
+int bh8_sink_submit(bh8_sink* sink, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* params);
+int bh8_sink_flush(bh8_sink* sink);
 /* Encode and append a BGR8 frame that is already in device memory (H * W * 3 bytes, device 0). */
 int bh8_sink_write_device(bh8_sink* sink, const void* d_bgr_frame);
 int bh8_sink_append_jpeg(bh8_sink* sink, const uint8_t* jpeg, size_t bytes);
@@ -239,6 +247,14 @@ int bh8_sink_stats(const bh8_sink* sink, uint64_t* frames, uint64_t* jpeg_bytes,
 const char* bh8_sink_last_error(const bh8_sink* sink);
 /* Finish the AVI (index, sizes), release everything; the handle is invalid afterwards. */
 int bh8_sink_close(bh8_sink* sink, uint64_t* file_bytes);
+
+/* One file from the per-GPU files of a frame-sharded job (host only, no GPU needed): frame k of the
+ * result is frame k / n_parts of part k % n_parts -- the round-robin ownership of whole frames that
+ * sharding.frames_of / bh8_render use -- so the merged video.avi has the frames in the order the
+ * reference's single loop would have written them.  The parts must agree in size and rate and their
+ * frame counts must be a round-robin split.  Errors: bh8_last_error(NULL). */
+int bh8_sink_merge(const char* const* part_paths, int n_parts, const char* out_path, uint64_t* frames,
+                   uint64_t* file_bytes);
 
 size_t bh8_pixel_bytes(int pixel_format);
 /* Bytes that travel host -> device per frame: the frame constants derived from the snapshot, passed as
