@@ -85,6 +85,45 @@ class Stats(C.Structure):
     ]
 
 
+OP_MOVE_X, OP_MOVE_Y, OP_MOVE_Z, OP_ROTATE_X, OP_ROTATE_Y, OP_ROTATE_Z, OP_MOVE_TO = range(7)
+TARGET_CAMERA = -1
+
+
+class Action(C.Structure):
+    """bh8_action: one Object::Move* / Rotate* call of a scripted animation (SURVEY 8f-3)."""
+    _fields_ = [
+        ("frame", C.c_int32),
+        ("target", C.c_int32),
+        ("op", C.c_int32),
+        ("reserved", C.c_int32),
+        ("amount", C.c_double),
+        ("to", Vec3),
+    ]
+
+
+class Basis(C.Structure):
+    _fields_ = [("vx", Vec3), ("vy", Vec3), ("vz", Vec3)]
+
+
+def reference_script(which, n_frames, disc_index):
+    """The reference's frame loop as a list of Actions (blackhole_solution_test.cc:346-407):
+      "cfg1_spin"        fixed camera; the disc spins RotateZ(pi/180) after every frame (:407)
+      "cfg3_flythrough"  BASELINE configs[3]: 'w' MoveX(+10) after frames 0-119, then 'L'
+                         RotateZ(+pi/1800*10) and 'd' MoveY(+10); plus the disc spin.
+    Must stay in step with oracle/ref_render.cc's replay (tools/make_flythrough.py made the golden states)."""
+    pi = 3.14159265358979323846
+    acts = []
+    for k in range(n_frames - 1):
+        if which == "cfg3_flythrough":
+            if k < 120:
+                acts.append(Action(k, TARGET_CAMERA, OP_MOVE_X, 0, 10.0))
+            else:
+                acts.append(Action(k, TARGET_CAMERA, OP_ROTATE_Z, 0, pi / 1800 * 10))
+                acts.append(Action(k, TARGET_CAMERA, OP_MOVE_Y, 0, 10.0))
+        acts.append(Action(k, disc_index, OP_ROTATE_Z, 0, pi / 180))
+    return acts
+
+
 def pixel_bytes(pixel_format):
     return 3 if pixel_format == PIXEL_BGR8 else 4
 

@@ -78,96 +78,141 @@ struct Bh8Frame {
   Bh8Obj obj[BH8_MAX_OBJECTS];
 };
 
-#if !defined(__CUDACC__) || defined(BH8_HOST_BUILD)
-// ---- host side: snapshot -> Bh8Frame --------------------------------------------------------
+// ---- snapshot -> Bh8Frame (host, and device for scripted animations: SURVEY.md 8f-3) ---------
+//
+// One definition for both sides.  On the device every operation goes through the round-to-nearest
+// intrinsics, which nvcc never contracts into FMAs, so a frame built by bh8_build_frames_kernel is
+// bit-identical to the one the host builds from the same snapshot (tests/test_gpu_script.py).
+#if defined(__CUDA_ARCH__)
+#define BH8F_HD __host__ __device__ inline
+#define BH8F_MUL(a, b) __dmul_rn((a), (b))
+#define BH8F_ADD(a, b) __dadd_rn((a), (b))
+#define BH8F_SUB(a, b) __dsub_rn((a), (b))
+#define BH8F_DIV(a, b) __ddiv_rn((a), (b))
+#define BH8F_SQRT(a) __dsqrt_rn(a)
+#else
+#if defined(__CUDACC__)
+#define BH8F_HD __host__ __device__ inline
+#else
+#define BH8F_HD static inline
+#endif
+#define BH8F_MUL(a, b) ((a) * (b))
+#define BH8F_ADD(a, b) ((a) + (b))
+#define BH8F_SUB(a, b) ((a) - (b))
+#define BH8F_DIV(a, b) ((a) / (b))
+#define BH8F_SQRT(a) sqrt(a)
+#endif
 
-static inline double bh8h_dot(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-static inline void bh8h_sub(double* r, const double* a, const double* b) {
-  for (int i = 0; i < 3; ++i) r[i] = a[i] - b[i];
+// cbrt(DBL_EPSILON) as glibc returns it (utility.h:17-21 epsilon<double>(); checked by tests/test_abi.py):
+// a literal, so that host and device start SolveG's interval from the same bits.
+#define BH8_CBRT_DBL_EPSILON 0x1.965fea53d6e3dp-18
+
+BH8F_HD double bh8h_dot(const double* a, const double* b) {
+  return BH8F_ADD(BH8F_ADD(BH8F_MUL(a[0], b[0]), BH8F_MUL(a[1], b[1])), BH8F_MUL(a[2], b[2]));
 }
-static inline void bh8h_cross(double* r, const double* a, const double* b) {
-  r[0] = a[1] * b[2] - a[2] * b[1];
-  r[1] = a[2] * b[0] - a[0] * b[2];
-  r[2] = a[0] * b[1] - a[1] * b[0];
+BH8F_HD void bh8h_sub(double* r, const double* a, const double* b) {
+  for (int i = 0; i < 3; ++i) r[i] = BH8F_SUB(a[i], b[i]);
 }
-static inline void bh8h_normalize(double* v) {  // cv::normalize semantics: zero stays zero
-  const double n = sqrt(bh8h_dot(v, v));
-  const double s = n ? 1. / n : 0.;
-  for (int i = 0; i < 3; ++i) v[i] *= s;
+BH8F_HD void bh8h_cross(double* r, const double* a, const double* b) {
+  r[0] = BH8F_SUB(BH8F_MUL(a[1], b[2]), BH8F_MUL(a[2], b[1]));
+  r[1] = BH8F_SUB(BH8F_MUL(a[2], b[0]), BH8F_MUL(a[0], b[2]));
+  r[2] = BH8F_SUB(BH8F_MUL(a[0], b[1]), BH8F_MUL(a[1], b[0]));
+}
+BH8F_HD void bh8h_normalize(double* v) {  // cv::normalize semantics: zero stays zero
+  const double n = BH8F_SQRT(bh8h_dot(v, v));
+  const double s = n ? BH8F_DIV(1., n) : 0.;
+  for (int i = 0; i < 3; ++i) v[i] = BH8F_MUL(v[i], s);
 }
 
-// tex_rows/tex_cols: sizes of the texture slots (0 = slot empty).  Returns BH8_OK or an error code
-// and a message in err (>= 160 bytes).
-static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
-                                  const int* tex_rows, const int* tex_cols, Bh8Frame* f, char* err) {
-#define BH8_FAIL(code, msg) \
-  do {                      \
-    strcpy(err, msg);       \
-    return code;            \
-  } while (0)
-  if (!scene || !cam || !prm || !scene->obj) BH8_FAIL(BH8_EINVAL, "null scene / camera / params");
-  if (scene->n_obj < 1 || scene->n_obj > BH8_MAX_OBJECTS) BH8_FAIL(BH8_EINVAL, "n_obj out of range");
+// Failure reasons of bh8_build_frame_core (index into bh8_frame_error_text / code).
+enum {
+  BH8F_OK = 0,
+  BH8F_NULL,
+  BH8F_NOBJ,
+  BH8F_TRACER,
+  BH8F_LINEAR_STEPS,
+  BH8F_BH_INDEX,
+  BH8F_CAMERA_SIZE,
+  BH8F_NSTEP,
+  BH8F_PIXEL_FORMAT,
+  BH8F_MASS,
+  BH8F_SHARDING,
+  BH8F_TWO_HOLES,
+  BH8F_PATTERN,
+  BH8F_CHESS_SIZE,
+  BH8F_KIND,
+  BH8F_TEXTURE,
+  BH8F_ZERO_NORMAL,
+  BH8F_N_ERRORS
+};
+
+// tex_rows/tex_cols: sizes of the texture slots (0 = slot empty).  Returns BH8F_OK or a BH8F_* reason.
+BH8F_HD int bh8_build_frame_core(const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
+                                 const int* tex_rows, const int* tex_cols, Bh8Frame* f) {
+  if (!scene || !cam || !prm || !scene->obj) return BH8F_NULL;
+  if (scene->n_obj < 1 || scene->n_obj > BH8_MAX_OBJECTS) return BH8F_NOBJ;
   const bool linear = prm->tracer == BH8_TRACER_LINEAR;
-  if (prm->tracer != BH8_TRACER_GEODESIC && !linear) BH8_FAIL(BH8_EINVAL, "unknown tracer");
-  if (linear && (prm->linear_steps < 1 || prm->linear_steps > 65535))
-    BH8_FAIL(BH8_EINVAL, "linear_steps must be in [1, 65535]");
+  if (prm->tracer != BH8_TRACER_GEODESIC && !linear) return BH8F_TRACER;
+  if (linear && (prm->linear_steps < 1 || prm->linear_steps > 65535)) return BH8F_LINEAR_STEPS;
   // The geodesic tracer bends rays around obj[bh_index]; the linear one needs no hole (bh_index may
   // be -1), and a StaticBlackhole in a flat-space scene is just a black sphere to FindCollision.
   if (!(linear && scene->bh_index == -1) &&
       (scene->bh_index < 0 || scene->bh_index >= scene->n_obj ||
        scene->obj[scene->bh_index].kind != BH8_KIND_BLACKHOLE))
-    BH8_FAIL(BH8_EINVAL, "bh_index does not name a BH8_KIND_BLACKHOLE object");
-  if (cam->width < 1 || cam->height < 1 || cam->width > 65536 || cam->height > 65536)
-    BH8_FAIL(BH8_EINVAL, "camera size out of range");
-  if (!linear && (prm->nstep < 2 || prm->nstep > 32767)) BH8_FAIL(BH8_EINVAL, "nstep must be in [2, 32767]");
-  if (prm->pixel_format < 0 || prm->pixel_format > BH8_PIXEL_BGR8) BH8_FAIL(BH8_EINVAL, "bad pixel_format");
-  static const bh8_object kNoHole = {BH8_KIND_BLACKHOLE, -1, -1, 0, {{0}}, {0}, {0}, {0}, 0, 0, 1.0, 0};
-  const bh8_object* bho = scene->bh_index >= 0 ? &scene->obj[scene->bh_index] : &kNoHole;
-  if (!(bho->mass > 0)) BH8_FAIL(BH8_EINVAL, "black hole mass must be positive");
+    return BH8F_BH_INDEX;
+  if (cam->width < 1 || cam->height < 1 || cam->width > 65536 || cam->height > 65536) return BH8F_CAMERA_SIZE;
+  if (!linear && (prm->nstep < 2 || prm->nstep > 32767)) return BH8F_NSTEP;
+  if (prm->pixel_format < 0 || prm->pixel_format > BH8_PIXEL_BGR8) return BH8F_PIXEL_FORMAT;
+  // no hole (linear tracer): a unit-mass stand-in at the origin feeds the (unused) geodesic constants
+  const double no_hole_pos[3] = {0.0, 0.0, 0.0};
+  const bh8_object* bho = scene->bh_index >= 0 ? &scene->obj[scene->bh_index] : nullptr;
+  const double bh_mass = bho ? bho->mass : 1.0;
+  const double* bh_pos = bho ? bho->v[0] : no_hole_pos;
+  if (!(bh_mass > 0)) return BH8F_MASS;
 
   memset(f, 0, sizeof *f);
   for (int i = 0; i < 3; ++i) {
     f->cam[i] = cam->pos[i];
-    f->fv[i] = cam->vx[i] * cam->focus_len;  // Camera::focus_vector, camera.h:61-63
+    f->fv[i] = BH8F_MUL(cam->vx[i], cam->focus_len);  // Camera::focus_vector, camera.h:61-63
     f->vy[i] = cam->vy[i];
     f->vz[i] = cam->vz[i];
-    f->bh[i] = bho->v[0][i];
+    f->bh[i] = bh_pos[i];
   }
-  f->half_w = cam->width / 2.0;
-  f->half_h = cam->height / 2.0;
+  f->half_w = BH8F_DIV((double)cam->width, 2.0);
+  f->half_h = BH8F_DIV((double)cam->height, 2.0);
   f->width = cam->width;
   f->height = cam->height;
   bh8h_sub(f->F, f->cam, f->bh);
   f->FF = bh8h_dot(f->F, f->F);
-  for (int i = 0; i < 3; ++i) f->Fhat[i] = f->F[i] / sqrt(f->FF);
+  for (int i = 0; i < 3; ++i) f->Fhat[i] = BH8F_DIV(f->F[i], BH8F_SQRT(f->FF));
   f->resolve_wait = 2;
-  f->mass = bho->mass;
-  f->two_m = 2.0 * bho->mass;
-  const double b_c = 3.0 * sqrt(3.0) * bho->mass;  // blackhole_solution.h:25
-  f->b_c2 = b_c * b_c;
-  f->inv3m = 1.0 / (3.0 * bho->mass);
-  f->R = 2 * bho->mass;  // radius(), blackhole_solution.h:57
-  f->R2 = f->R * f->R;
-  f->r0 = sqrt(f->FF);
-  f->u0 = 1. / f->r0;
+  f->mass = bh_mass;
+  f->two_m = BH8F_MUL(2.0, bh_mass);
+  const double b_c = BH8F_MUL(BH8F_MUL(3.0, 1.7320508075688772 /* sqrt(3.0) */), bh_mass);  // blackhole_solution.h:25
+  f->b_c2 = BH8F_MUL(b_c, b_c);
+  f->inv3m = BH8F_DIV(1.0, BH8F_MUL(3.0, bh_mass));
+  f->R = BH8F_MUL(2.0, bh_mass);  // radius(), blackhole_solution.h:57
+  f->R2 = BH8F_MUL(f->R, f->R);
+  f->r0 = BH8F_SQRT(f->FF);
+  f->u0 = BH8F_DIV(1., f->r0);
   {  // SolveG's interval, blackhole_solution.h:37-38; utility.h:17-21
-    const double l = 0.0 + cbrt(2.220446049250313e-16);
+    const double l = BH8F_ADD(0.0, BH8_CBRT_DBL_EPSILON);
     const double r = f->inv3m;
-    f->bis_mid0 = (l + r) / 2.0;
+    f->bis_mid0 = BH8F_DIV(BH8F_ADD(l, r), 2.0);
     f->bis_l0 = l;
-    f->bis_grid = (r - l) / 1048576.0;
-    f->bis_inv_grid = 1048576.0 / (r - l);
-    f->nine_m2 = 9.0 * bho->mass * bho->mass;
-    double h = (r - l) / 2.0;
+    f->bis_grid = BH8F_DIV(BH8F_SUB(r, l), 1048576.0);
+    f->bis_inv_grid = BH8F_DIV(1048576.0, BH8F_SUB(r, l));
+    f->nine_m2 = BH8F_MUL(BH8F_MUL(9.0, bh_mass), bh_mass);
+    double h = BH8F_DIV(BH8F_SUB(r, l), 2.0);
     for (int i = 0; i <= BH8_BISECT_ITERS; ++i) {
-      h /= 2.0;
+      h = BH8F_DIV(h, 2.0);
       f->bis_h[i] = h;  // bis_h[i] = (r-l)/2^(i+2)
     }
   }
   f->tracer = prm->tracer;
   f->linear_steps = prm->linear_steps;
   f->nstep = linear ? 2 : prm->nstep;
-  f->inv_nstep = 1.0 / f->nstep;
+  f->inv_nstep = BH8F_DIV(1.0, (double)f->nstep);
   f->n_obj = scene->n_obj;
   f->bh_index = scene->bh_index;
   f->pixel_format = prm->pixel_format;
@@ -176,7 +221,7 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
   f->shard_count = prm->shard_count;
   f->flags = prm->flags;
   if (f->shard_count > 1 && (f->shard_index < 0 || f->shard_index >= f->shard_count || f->stripe_rows < 1))
-    BH8_FAIL(BH8_EINVAL, "bad stripe sharding parameters");
+    return BH8F_SHARDING;
 
   double min_dist = INFINITY, max_n = 0.0, max_c = 0.0;
   for (int k = 0; k < scene->n_obj; ++k) {
@@ -190,8 +235,7 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
       case BH8_KIND_BLACKHOLE:
         q->cls = BH8_CLASS_HORIZON;
         f->hole_mask |= 1u << k;
-        if (k != scene->bh_index)
-          BH8_FAIL(BH8_EUNSUPPORTED, "more than one black hole in a scene is not supported");
+        if (k != scene->bh_index) return BH8F_TWO_HOLES;
         for (int i = 0; i < 3; ++i) q->p0[i] = o->v[0][i];
         continue;
       case BH8_KIND_ANNULUS:
@@ -215,8 +259,7 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
         break;
       case BH8_KIND_INFINITE_PLANE:
         q->cls = BH8_CLASS_OBJECT;
-        if (o->pattern != BH8_PATTERN_BLACK && o->pattern != BH8_PATTERN_CHESS)
-          BH8_FAIL(BH8_EUNSUPPORTED, "InfinitePlane pattern is not BLACK or CHESS (opaque std::function)");
+        if (o->pattern != BH8_PATTERN_BLACK && o->pattern != BH8_PATTERN_CHESS) return BH8F_PATTERN;
         for (int i = 0; i < 3; ++i) {
           q->n[i] = o->n[i];      // vector_z(), vector_object.h:211
           q->p0[i] = o->v[0][i];  // position()
@@ -226,11 +269,10 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
         q->ey0 = o->ey[0];
         q->ey1 = o->ey[1];
         q->psize = o->pattern_size;
-        if (o->pattern == BH8_PATTERN_CHESS && !((int)(o->pattern_size * 2) != 0))
-          BH8_FAIL(BH8_EINVAL, "chess pattern_size too small: (int)(2*size) == 0 divides by zero in the reference");
+        if (o->pattern == BH8_PATTERN_CHESS && !((int)BH8F_MUL(o->pattern_size, 2.0) != 0)) return BH8F_CHESS_SIZE;
         break;
       default:
-        BH8_FAIL(BH8_EUNSUPPORTED, "object kind not supported by the GPU path (Triangle/Sphere/Cylinder)");
+        return BH8F_KIND;
     }
     q->d = bh8h_dot(q->n, q->p0);
     {
@@ -246,15 +288,14 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
       bh8h_sub(q->s1, o->v[2], o->v[1]);
       bh8h_sub(s2, o->v[4], o->v[1]);
       const double s1s1 = bh8h_dot(q->s1, q->s1);
-      q->inv_s1s1 = 1.0 / s1s1;
+      q->inv_s1s1 = BH8F_DIV(1.0, s1s1);
       if (o->tex_id >= 0) {
-        if (o->tex_id >= BH8_MAX_TEXTURES || !tex_rows || tex_rows[o->tex_id] <= 0)
-          BH8_FAIL(BH8_EINVAL, "object refers to a texture slot that was never set");
+        if (o->tex_id >= BH8_MAX_TEXTURES || !tex_rows || tex_rows[o->tex_id] <= 0) return BH8F_TEXTURE;
         q->tex = o->tex_id;
         q->tex_rows = tex_rows[o->tex_id];
         q->tex_cols = tex_cols[o->tex_id];
-        q->kw = q->tex_cols / s1s1;
-        q->kh = q->tex_rows / sqrt(bh8h_dot(s2, s2));
+        q->kw = BH8F_DIV((double)q->tex_cols, s1s1);
+        q->kh = BH8F_DIV((double)q->tex_rows, BH8F_SQRT(bh8h_dot(s2, s2)));
       }
     }
     double wc[3];
@@ -273,24 +314,63 @@ static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam,
       f->nc_c[j] = (float)q->c_bh;
       if (side_cam > 0) f->nc_cam_bits |= 1u << j;
       if (side_cam < 0) f->nc_cam_bits |= 1u << (16 + j);
-      const double nn = sqrt(bh8h_dot(q->n, q->n));  // 1 for the reference's shapes; not relied upon
-      if (!(nn > 0)) BH8_FAIL(BH8_EINVAL, "plane with a zero normal");
-      if (fabs(q->c_bh) / nn < min_dist) min_dist = fabs(q->c_bh) / nn;
+      const double nn = BH8F_SQRT(bh8h_dot(q->n, q->n));  // 1 for the reference's shapes; not relied upon
+      if (!(nn > 0)) return BH8F_ZERO_NORMAL;
+      if (BH8F_DIV(fabs(q->c_bh), nn) < min_dist) min_dist = BH8F_DIV(fabs(q->c_bh), nn);
       if (nn > max_n) max_n = nn;
       if (fabs(q->c_bh) > max_c) max_c = fabs(q->c_bh);
     }
   }
-  f->lease_kphi = f->noncentral_mask ? (float)(0.4995 / max_n) : 0.0f;
-  f->lease_ku = f->noncentral_mask ? (float)(0.24975 / max_c) : 0.0f;
+  f->lease_kphi = f->noncentral_mask ? (float)BH8F_DIV(0.4995, max_n) : 0.0f;
+  f->lease_ku = f->noncentral_mask ? (float)BH8F_DIV(0.24975, max_c) : 0.0f;
   // A chord between two points of the ray stays inside radius max(r1,r2); a plane at distance D
   // from the hole can only be met when max(r1,r2) >= D, i.e. min(u1,u2) <= 1/D (small margin).
-  f->u_gate = f->noncentral_mask ? (1.0 + 1e-9) / min_dist : -1.0;
+  f->u_gate = f->noncentral_mask ? BH8F_DIV(BH8F_ADD(1.0, 1e-9), min_dist) : -1.0;
   // Horizon sphere R = 2M: a chord whose ends are both outside 1.5R and subtend <= 1 rad stays
   // outside R (1.5 cos(0.5) = 1.316 > 1).
-  f->u_horizon = 1.0 / (1.5 * f->R * (1.0 + 1e-9));
+  f->u_horizon = BH8F_DIV(1.0, BH8F_MUL(BH8F_MUL(1.5, f->R), BH8F_ADD(1.0, 1e-9)));
   if (!(f->u0 <= f->u_horizon)) f->first_resolve = 1;
-  return BH8_OK;
-#undef BH8_FAIL
+  return BH8F_OK;
+}
+
+#if !defined(__CUDACC__) || defined(BH8_HOST_BUILD)
+// ---- host side: reasons -> error codes and messages ---------------------------------------------
+static inline int bh8_frame_error_code(int reason) {
+  switch (reason) {
+    case BH8F_OK: return BH8_OK;
+    case BH8F_TWO_HOLES:
+    case BH8F_PATTERN:
+    case BH8F_KIND: return BH8_EUNSUPPORTED;
+    default: return BH8_EINVAL;
+  }
+}
+static inline const char* bh8_frame_error_text(int reason) {
+  static const char* const kText[BH8F_N_ERRORS] = {
+      "ok",
+      "null scene / camera / params",
+      "n_obj out of range",
+      "unknown tracer",
+      "linear_steps must be in [1, 65535]",
+      "bh_index does not name a BH8_KIND_BLACKHOLE object",
+      "camera size out of range",
+      "nstep must be in [2, 32767]",
+      "bad pixel_format",
+      "black hole mass must be positive",
+      "bad stripe sharding parameters",
+      "more than one black hole in a scene is not supported",
+      "InfinitePlane pattern is not BLACK or CHESS (opaque std::function)",
+      "chess pattern_size too small: (int)(2*size) == 0 divides by zero in the reference",
+      "object kind not supported by the GPU path (Triangle/Sphere/Cylinder)",
+      "object refers to a texture slot that was never set",
+      "plane with a zero normal"};
+  return reason >= 0 && reason < BH8F_N_ERRORS ? kText[reason] : "unknown frame error";
+}
+// Returns BH8_OK or an error code and a message in err (>= 160 bytes).
+static inline int bh8_build_frame(const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
+                                  const int* tex_rows, const int* tex_cols, Bh8Frame* f, char* err) {
+  const int reason = bh8_build_frame_core(scene, cam, prm, tex_rows, tex_cols, f);
+  if (reason != BH8F_OK) strcpy(err, bh8_frame_error_text(reason));
+  return bh8_frame_error_code(reason);
 }
 #endif  // host
 

@@ -174,9 +174,11 @@ __device__ __forceinline__ void store_pixel(const Bh8Frame& f, const Bh8Out& out
   }
 }
 
+// One 32x8 tile of the frame.  `f` is in the constant bank either way -- a __grid_constant__ kernel
+// parameter (bh8_render_kernel) or the __constant__ frame a script renders from
+// (bh8_render_kernel_script) -- so its fields are direct operands of the FP64 instructions.
 template <int NN>
-__global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
-bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
+__device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex, const Bh8Out& out) {
   __shared__ __align__(16) uint32_t sh_rgba[kThreads];
   __shared__ unsigned long long sh_red[7];
   const int tid = threadIdx.x;
@@ -264,10 +266,26 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
   store_pixel(f, out, sh_rgba, sh_red, tid, lane, slot, x0, y0, x, y, inside, bgr, oob, cls, key, steps);
 }
 
+template <int NN>
+__global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
+bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
+  render_tile<NN>(f, tex, out);
+}
+
+// Scripted animation: the frame constants were built ON THE DEVICE
+// (bh8_build_frames_kernel) and are copied device-to-device into this symbol in stream order right
+// before the launch; no per-frame data comes from the host.
+__constant__ Bh8Frame c_script_frame;
+
+template <int NN>
+__global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
+bh8_render_kernel_script(const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
+  render_tile<NN>(c_script_frame, tex, out);
+}
+
 // Flat-space tracer (BH8_TRACER_LINEAR): one thread per pixel, at most linear_steps segment tests,
 // same tile mapping, colour and store path as the geodesic kernel.
-__global__ void __launch_bounds__(kThreads, 4)
-bh8_linear_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
+__device__ __forceinline__ void linear_tile(const Bh8Frame& f, const Bh8Tex& tex, const Bh8Out& out) {
   __shared__ __align__(16) uint32_t sh_rgba[kThreads];
   __shared__ unsigned long long sh_red[7];
   const int tid = threadIdx.x;
@@ -300,6 +318,16 @@ bh8_linear_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
     key = f.obj[hit].key;
   }
   store_pixel(f, out, sh_rgba, sh_red, tid, lane, slot, x0, y0, x, y, inside, bgr, oob, cls, key, steps);
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+bh8_linear_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
+  linear_tile(f, tex, out);
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+bh8_linear_kernel_script(const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
+  linear_tile(c_script_frame, tex, out);
 }
 
 // Precision study: the bare geodesic update chain (u += du; G; rsqrt; trapezoid; two compares) for

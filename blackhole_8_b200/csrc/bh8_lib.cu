@@ -704,3 +704,4 @@ int bh8_measure_fp64_peak(bh8_ctx* ctx, double* flops_per_s, double* seconds_run
 }  // extern "C"
 
 #include "bh8_sink.h"
+#include "bh8_script.h"

@@ -1,0 +1,234 @@
+// bh8_script.h -- scripted animation behind bh8_script_* (SURVEY.md 8f-3): host side of bh8_anim.cuh.
+//
+// Included at the end of bh8_lib.cu (one translation unit: it uses bh8_ctx, Device, make_grid).
+#ifndef BH8_SCRIPT_H_
+#define BH8_SCRIPT_H_
+
+#include <vector>
+
+#include "bh8_anim.cuh"
+
+struct bh8_script {
+  bh8_ctx* ctx = nullptr;
+  int n_frames = 0, n_obj = 0, bh_index = -1;
+  bh8_params prm{};
+  int width = 0, height = 0;
+  Bh8Frame* d_frames = nullptr;
+  bh8_camera* d_cams = nullptr;
+  bh8_object* d_objs = nullptr;
+  std::vector<int> n_nc;  // per frame: which instantiation of the render kernel it takes
+};
+
+namespace {
+
+template <int NN>
+void launch_script_kernel(dim3 grid, cudaStream_t st, const bh8::Bh8Tex& tex, const bh8::Bh8Out& out) {
+  bh8::bh8_render_kernel_script<NN><<<grid, bh8::kThreads, 0, st>>>(tex, out);
+}
+
+void script_free(bh8_script* s) {
+  if (!s) return;
+  if (s->ctx && cudaSetDevice(s->ctx->dev[0].ordinal) == cudaSuccess) {
+    cudaStreamSynchronize(s->ctx->dev[0].stream);
+    cudaFree(s->d_frames);
+    cudaFree(s->d_cams);
+    cudaFree(s->d_objs);
+  }
+  delete s;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t bh8_frame_bytes(void) { return sizeof(Bh8Frame); }
+
+int bh8_host_frame_constants(const bh8_ctx* ctx, const bh8_scene* scene, const bh8_camera* cam,
+                             const bh8_params* params, void* out, size_t bytes) {
+  if (!ctx || !out || bytes != sizeof(Bh8Frame)) return BH8_EINVAL;
+  Bh8Frame f;
+  char msg[192];
+  const int rc = bh8_build_frame(scene, cam, params, ctx->tex_rows, ctx->tex_cols, &f, msg);
+  if (rc != BH8_OK) return fail(const_cast<bh8_ctx*>(ctx), rc, msg);
+  if (params->flags & BH8_FLAG_NO_BATCHING) f.resolve_wait = -1;
+  std::memcpy(out, &f, sizeof f);
+  return BH8_OK;
+}
+
+int bh8_script_create(bh8_ctx* ctx, const bh8_scene* scene0, const bh8_basis* obj_basis, const bh8_camera* cam0,
+                      const bh8_params* params, const bh8_action* actions, int n_actions, int n_frames,
+                      bh8_script** out) {
+  if (!ctx) return BH8_EINVAL;
+  if (!out) return fail(ctx, BH8_EINVAL, "bh8_script_create: null out");
+  *out = nullptr;
+  if (!scene0 || !scene0->obj || !cam0 || !params || n_frames < 1 || n_frames > (1 << 24) || n_actions < 0 ||
+      (n_actions > 0 && !actions))
+    return fail(ctx, BH8_EINVAL, "bad arguments to bh8_script_create");
+  if (scene0->n_obj < 1 || scene0->n_obj > BH8_MAX_OBJECTS) return fail(ctx, BH8_EINVAL, "n_obj out of range");
+  const int n_obj = scene0->n_obj;
+  {  // frame 0 must be a valid scene: the common mistakes get their message before anything is launched
+    Bh8Frame f;
+    char msg[192];
+    const int rc = bh8_build_frame(scene0, cam0, params, ctx->tex_rows, ctx->tex_cols, &f, msg);
+    if (rc != BH8_OK) return fail(ctx, rc, msg);
+  }
+  std::vector<Bh8Action> acts(static_cast<size_t>(n_actions) + 1);
+  if (const char* why = bh8a_prepare_actions(actions, n_actions, n_obj, acts.data())) return fail(ctx, BH8_EINVAL, why);
+  std::vector<Bh8Entity> ent(static_cast<size_t>(n_obj) + 1);
+  bh8a_prepare_entities(scene0, obj_basis, cam0, ent.data());
+
+  Device& d = ctx->dev[0];
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  bh8_script* s = new (std::nothrow) bh8_script();
+  if (!s) return fail(ctx, BH8_ENOMEM, "out of host memory");
+  s->ctx = ctx;
+  s->n_frames = n_frames;
+  s->n_obj = n_obj;
+  s->bh_index = scene0->bh_index;
+  s->prm = *params;
+  s->width = cam0->width;
+  s->height = cam0->height;
+  Bh8Entity* d_ent = nullptr;
+  Bh8Action* d_act = nullptr;
+  bh8_object* d_proto = nullptr;
+  int* d_status = nullptr;
+  std::vector<int> status(2 * static_cast<size_t>(n_frames));
+  cudaError_t e = cudaSuccess;
+  const auto step = [&](cudaError_t r) {
+    if (e == cudaSuccess) e = r;
+    return e == cudaSuccess;
+  };
+  step(cudaMalloc(reinterpret_cast<void**>(&d_ent), ent.size() * sizeof(Bh8Entity))) &&
+      step(cudaMalloc(reinterpret_cast<void**>(&d_act), acts.size() * sizeof(Bh8Action))) &&
+      step(cudaMalloc(reinterpret_cast<void**>(&d_proto), n_obj * sizeof(bh8_object))) &&
+      step(cudaMalloc(reinterpret_cast<void**>(&d_status), status.size() * sizeof(int))) &&
+      step(cudaMalloc(reinterpret_cast<void**>(&s->d_cams), static_cast<size_t>(n_frames) * sizeof(bh8_camera))) &&
+      step(cudaMalloc(reinterpret_cast<void**>(&s->d_objs), static_cast<size_t>(n_frames) * n_obj * sizeof(bh8_object))) &&
+      step(cudaMalloc(reinterpret_cast<void**>(&s->d_frames), static_cast<size_t>(n_frames) * sizeof(Bh8Frame))) &&
+      step(cudaMemcpyAsync(d_ent, ent.data(), ent.size() * sizeof(Bh8Entity), cudaMemcpyHostToDevice, d.stream)) &&
+      step(cudaMemcpyAsync(d_act, acts.data(), acts.size() * sizeof(Bh8Action), cudaMemcpyHostToDevice, d.stream)) &&
+      step(cudaMemcpyAsync(d_proto, scene0->obj, n_obj * sizeof(bh8_object), cudaMemcpyHostToDevice, d.stream));
+  if (e == cudaSuccess) {
+    bh8::bh8_animate_kernel<<<1, 32, 0, d.stream>>>(d_ent, d_act, n_actions, n_obj, n_frames, d_proto, *cam0, s->d_cams,
+                                                    s->d_objs);
+    step(cudaGetLastError());
+    bh8::Bh8TexSizes ts;
+    for (int i = 0; i < BH8_MAX_TEXTURES; ++i) {
+      ts.rows[i] = ctx->tex_rows[i];
+      ts.cols[i] = ctx->tex_cols[i];
+    }
+    int resolve_wait = 0x7fffffff;
+    if (const char* w = std::getenv("BH8_RESOLVE_WAIT")) resolve_wait = std::atoi(w);  // tuning knob, as launch_frame
+    if (e == cudaSuccess) {
+      bh8::bh8_build_frames_kernel<<<(n_frames + 63) / 64, 64, 0, d.stream>>>(
+          s->d_cams, s->d_objs, n_obj, s->bh_index, s->prm, ts, resolve_wait, s->d_frames, d_status, n_frames);
+      step(cudaGetLastError());
+      ctx->launches += 2;
+    }
+    step(cudaMemcpyAsync(status.data(), d_status, status.size() * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+    step(cudaStreamSynchronize(d.stream));
+  }
+  cudaFree(d_ent);
+  cudaFree(d_act);
+  cudaFree(d_proto);
+  cudaFree(d_status);
+  if (e != cudaSuccess) {
+    script_free(s);
+    return fail(ctx, BH8_ECUDA, std::string("bh8_script_create: ") + cudaGetErrorString(e));
+  }
+  s->n_nc.resize(n_frames);
+  for (int k = 0; k < n_frames; ++k) {
+    if (status[2 * k] != BH8F_OK) {
+      const int reason = status[2 * k];
+      script_free(s);
+      return fail(ctx, bh8_frame_error_code(reason),
+                  "bh8_script_create: frame " + std::to_string(k) + ": " + bh8_frame_error_text(reason));
+    }
+    s->n_nc[k] = status[2 * k + 1];
+  }
+  *out = s;
+  return BH8_OK;
+}
+
+int bh8_script_frames(const bh8_script* s) { return s ? s->n_frames : 0; }
+
+int bh8_script_render(bh8_script* s, int frame, void* d_pixels, void* d_class, void* d_key, void* d_steps) {
+  if (!s) return BH8_EINVAL;
+  bh8_ctx* ctx = s->ctx;
+  if (frame < 0 || frame >= s->n_frames) return fail(ctx, BH8_EINVAL, "bh8_script_render: frame out of range");
+  if (!d_pixels) return fail(ctx, BH8_EINVAL, "null pixel buffer");
+  Device& d = ctx->dev[0];
+  Bh8Frame shape;  // make_grid reads the frame size and the stripe sharding only
+  shape.width = s->width;
+  shape.height = s->height;
+  shape.stripe_rows = s->prm.stripe_rows;
+  shape.shard_index = s->prm.shard_index;
+  shape.shard_count = s->prm.shard_count;
+  dim3 grid;
+  if (make_grid(shape, &grid) != BH8_OK)
+    return fail(ctx, BH8_EINVAL, "stripe_rows must be a multiple of 8 when shard_count > 1");
+  if (grid.y == 0) return BH8_OK;
+  bh8::Bh8Tex tex;
+  for (int i = 0; i < BH8_MAX_TEXTURES; ++i) tex.obj[i] = d.tex_obj[i];
+  bh8::Bh8Out out;
+  out.pixels = static_cast<uint8_t*>(d_pixels);
+  out.cls = static_cast<uint8_t*>(d_class);
+  out.key = static_cast<int8_t*>(d_key);
+  out.steps = static_cast<uint16_t*>(d_steps);
+  out.stats = d.d_stats;
+  out.vec_ok = (s->width % 4 == 0) && (reinterpret_cast<uintptr_t>(d_pixels) % 16 == 0) &&
+               s->prm.pixel_format != BH8_PIXEL_BGR8;
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  // Frame constants: device -> constant bank, in stream order (after the previous frame's kernel).
+  BH8_CUDA(ctx, cudaMemcpyToSymbolAsync(bh8::c_script_frame, s->d_frames + frame, sizeof(Bh8Frame), 0,
+                                        cudaMemcpyDeviceToDevice, d.stream));
+  if (s->prm.tracer == BH8_TRACER_LINEAR) {
+    bh8::bh8_linear_kernel_script<<<grid, bh8::kThreads, 0, d.stream>>>(tex, out);
+  } else {
+    const int nn = s->n_nc[frame];
+    switch (nn <= bh8::kMaxFilterPlanes ? nn : -1) {
+      case 0: launch_script_kernel<0>(grid, d.stream, tex, out); break;
+      case 1: launch_script_kernel<1>(grid, d.stream, tex, out); break;
+      case 2: launch_script_kernel<2>(grid, d.stream, tex, out); break;
+      case 3: launch_script_kernel<3>(grid, d.stream, tex, out); break;
+      case 4: launch_script_kernel<4>(grid, d.stream, tex, out); break;
+      default: launch_script_kernel<-1>(grid, d.stream, tex, out); break;
+    }
+  }
+  BH8_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return BH8_OK;
+}
+
+int bh8_script_state(bh8_script* s, int frame, bh8_camera* cam, bh8_object* objs) {
+  if (!s) return BH8_EINVAL;
+  bh8_ctx* ctx = s->ctx;
+  if (frame < 0 || frame >= s->n_frames) return fail(ctx, BH8_EINVAL, "bh8_script_state: frame out of range");
+  Device& d = ctx->dev[0];
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  if (cam)
+    BH8_CUDA(ctx, cudaMemcpyAsync(cam, s->d_cams + frame, sizeof(bh8_camera), cudaMemcpyDeviceToHost, d.stream));
+  if (objs)
+    BH8_CUDA(ctx, cudaMemcpyAsync(objs, s->d_objs + static_cast<size_t>(frame) * s->n_obj,
+                                  s->n_obj * sizeof(bh8_object), cudaMemcpyDeviceToHost, d.stream));
+  BH8_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return BH8_OK;
+}
+
+int bh8_script_frame_constants(bh8_script* s, int frame, void* out, size_t bytes) {
+  if (!s) return BH8_EINVAL;
+  bh8_ctx* ctx = s->ctx;
+  if (frame < 0 || frame >= s->n_frames || !out || bytes != sizeof(Bh8Frame))
+    return fail(ctx, BH8_EINVAL, "bad arguments to bh8_script_frame_constants");
+  Device& d = ctx->dev[0];
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  BH8_CUDA(ctx, cudaMemcpyAsync(out, s->d_frames + frame, sizeof(Bh8Frame), cudaMemcpyDeviceToHost, d.stream));
+  BH8_CUDA(ctx, cudaStreamSynchronize(d.stream));
+  return BH8_OK;
+}
+
+void bh8_script_destroy(bh8_script* s) { script_free(s); }
+
+}  // extern "C"
+
+#endif  // BH8_SCRIPT_H_

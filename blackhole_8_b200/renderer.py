@@ -64,6 +64,16 @@ def load_library(path=None):
         "bh8_host_free": (i32, [vp]),
         "bh8_measure_fp64_peak": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "bh8_measure_stepping": (i32, [vp, i32, C.POINTER(C.c_double)]),
+        "bh8_script_create": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Basis), C.POINTER(abi.Camera),
+                                    C.POINTER(abi.Params), C.POINTER(abi.Action), i32, i32, C.POINTER(vp)]),
+        "bh8_script_frames": (i32, [vp]),
+        "bh8_script_render": (i32, [vp, i32, vp, vp, vp, vp]),
+        "bh8_script_state": (i32, [vp, i32, C.POINTER(abi.Camera), C.POINTER(abi.Object)]),
+        "bh8_script_frame_constants": (i32, [vp, i32, vp, C.c_size_t]),
+        "bh8_host_frame_constants": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params),
+                                           vp, C.c_size_t]),
+        "bh8_frame_bytes": (C.c_size_t, []),
+        "bh8_script_destroy": (None, [vp]),
         "bh8_sink_open": (i32, [vp, C.c_char_p, i32, i32, C.c_double, i32, C.POINTER(vp)]),
         "bh8_sink_render": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params)]),
         "bh8_sink_submit": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params)]),
@@ -257,6 +267,14 @@ class Renderer:
     def pinned(self, shape, dtype=np.uint8):
         return PinnedBuffer(self.lib, shape, dtype)
 
+    def host_frame_constants(self, snap, nstep=None, pixel_format=abi.PIXEL_RGBA8, flags=0):
+        """The frame constants the host derives from a snapshot (what every non-scripted launch passes)."""
+        prm = snap.params(pixel_format, flags, nstep)
+        buf = (C.c_uint8 * self.lib.bh8_frame_bytes())()
+        self._check(self.lib.bh8_host_frame_constants(self._ctx, C.byref(snap.scene), C.byref(snap.camera),
+                                                      C.byref(prm), buf, len(buf)))
+        return bytes(buf)
+
     def measure_stepping(self, fp32):
         v = C.c_double()
         self._check(self.lib.bh8_measure_stepping(self._ctx, 1 if fp32 else 0, C.byref(v)))
@@ -266,6 +284,53 @@ class Renderer:
         f, s = C.c_double(), C.c_double()
         self._check(self.lib.bh8_measure_fp64_peak(self._ctx, C.byref(f), C.byref(s)))
         return f.value, s.value
+
+
+class Script:
+    """A scripted animation replayed and rendered on the GPU (bh8_script_*): the reference's
+    per-frame Camera::Move*/Rotate* and Annulus::RotateZ calls (blackhole_solution_test.cc:346-407) as a
+    list of abi.Action.  After construction no per-frame data comes from the host."""
+
+    def __init__(self, renderer, snap0, actions, n_frames, basis=None, nstep=None, pixel_format=abi.PIXEL_RGBA8,
+                 flags=0, stripe_rows=0, shard_index=0, shard_count=0):
+        self._r = renderer
+        self.lib = renderer.lib
+        self._h = C.c_void_p()
+        self.n_obj = snap0.scene.n_obj
+        self.snap0 = snap0
+        prm = snap0.params(pixel_format, flags, nstep, stripe_rows, shard_index, shard_count)
+        acts = (abi.Action * max(1, len(actions)))(*actions)
+        bas = (abi.Basis * self.n_obj)(*basis) if basis is not None else None
+        renderer._check(self.lib.bh8_script_create(renderer._ctx, C.byref(snap0.scene), bas, C.byref(snap0.camera),
+                                                   C.byref(prm), acts, len(actions), n_frames, C.byref(self._h)))
+        self.n_frames = n_frames
+
+    def render(self, frame, d_pixels, d_cls=None, d_key=None, d_steps=None):
+        self._r._check(self.lib.bh8_script_render(self._h, frame, C.c_void_p(d_pixels), C.c_void_p(d_cls),
+                                                  C.c_void_p(d_key), C.c_void_p(d_steps)))
+
+    def state(self, frame):
+        """(abi.Camera, [abi.Object]) of frame `frame`, read back from the device."""
+        cam = abi.Camera()
+        objs = (abi.Object * self.n_obj)()
+        self._r._check(self.lib.bh8_script_state(self._h, frame, C.byref(cam), objs))
+        return cam, list(objs)
+
+    def frame_constants(self, frame):
+        buf = (C.c_uint8 * self.lib.bh8_frame_bytes())()
+        self._r._check(self.lib.bh8_script_frame_constants(self._h, frame, buf, len(buf)))
+        return bytes(buf)
+
+    def close(self):
+        if self._h:
+            self.lib.bh8_script_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 class VideoSink:

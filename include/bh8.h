@@ -256,6 +256,63 @@ int bh8_sink_close(bh8_sink* sink, uint64_t* file_bytes);
 int bh8_sink_merge(const char* const* part_paths, int n_parts, const char* out_path, uint64_t* frames,
                    uint64_t* file_bytes);
 
+/* ---- Scene / camera animation on the device -----------------------------------
+ * The reference animates on the host between frames: key handlers call Camera::MoveX / RotateZ / ...
+ * and the disc spins by Annulus::RotateZ(pi/180) after every frame (blackhole_solution_test.cc:346-407;
+ * Object::Move* / Rotate*, object/object.h:58-88; RotationMatrixForAxis, matrix.h:342-356).  A script
+ * is that sequence written down: bh8_script_create() replays it ON THE GPU (bit-identical to the
+ * reference's classes), leaves one camera + object snapshot per frame in device memory and derives
+ * every frame's constants there as well; bh8_script_render() then draws frame k without any per-frame
+ * host data (no host replay, no snapshot upload). */
+enum {
+  BH8_OP_MOVE_X = 0,   /* Object::MoveX(amount): every vertex += vector_x() * amount */
+  BH8_OP_MOVE_Y = 1,
+  BH8_OP_MOVE_Z = 2,
+  BH8_OP_ROTATE_X = 3, /* Object::RotateX(amount): about vector_x() through position() */
+  BH8_OP_ROTATE_Y = 4,
+  BH8_OP_ROTATE_Z = 5,
+  BH8_OP_MOVE_TO = 6   /* Object::MoveTo(to): vertex()[0] = to (the other vertices stay, as in the reference) */
+};
+#define BH8_TARGET_CAMERA (-1)
+
+typedef struct bh8_action {
+  int32_t frame;   /* applied AFTER frame `frame` is drawn, i.e. it shapes frame + 1 (the reference draws,
+                      then handles the key and spins the disc); actions must be sorted by frame, actions of
+                      one frame apply in list order */
+  int32_t target;  /* BH8_TARGET_CAMERA or an index into scene->obj */
+  int32_t op;      /* BH8_OP_* */
+  int32_t reserved;
+  double amount;   /* distance, or angle in radians */
+  double to[3];    /* BH8_OP_MOVE_TO */
+} bh8_action;
+
+typedef struct bh8_basis { /* Object::vector_x/y/z() of an object at frame 0 */
+  double vx[3], vy[3], vz[3];
+} bh8_basis;
+
+typedef struct bh8_script bh8_script;
+
+/* scene0 / cam0: the state at frame 0.  obj_basis: n_obj entries, or NULL for the basis every shape
+ * the reference's drivers build has -- (1,0,0),(0,1,0),(0,0,1) -- except INFINITE_PLANE objects, whose
+ * basis is their (ex, ey, n).  params: as for bh8_render_device (nstep, pixel format, sharding, tracer).
+ * Runs on device 0 of the context; synchronous (it reports a frame whose scene is invalid). */
+int bh8_script_create(bh8_ctx* ctx, const bh8_scene* scene0, const bh8_basis* obj_basis, const bh8_camera* cam0,
+                      const bh8_params* params, const bh8_action* actions, int n_actions, int n_frames,
+                      bh8_script** out);
+int bh8_script_frames(const bh8_script* script);
+/* Draw frame `frame` into device buffers (as bh8_render_device; d_class / d_key / d_steps nullable).
+ * Asynchronous on the context's stream; bh8_sync() waits. */
+int bh8_script_render(bh8_script* script, int frame, void* d_pixels, void* d_class, void* d_key, void* d_steps);
+/* Read frame `frame`'s snapshot back: cam (nullable) and objs (nullable, n_obj entries). */
+int bh8_script_state(bh8_script* script, int frame, bh8_camera* cam, bh8_object* objs);
+/* Verification hook: the device-built frame constants of frame `frame` (bytes = bh8_frame_bytes()) and
+ * the ones the host derives from a snapshot -- the two must be identical. */
+int bh8_script_frame_constants(bh8_script* script, int frame, void* out, size_t bytes);
+int bh8_host_frame_constants(const bh8_ctx* ctx, const bh8_scene* scene, const bh8_camera* cam,
+                             const bh8_params* params, void* out, size_t bytes);
+size_t bh8_frame_bytes(void);
+void bh8_script_destroy(bh8_script* script);
+
 size_t bh8_pixel_bytes(int pixel_format);
 /* Bytes that travel host -> device per frame: the frame constants derived from the snapshot, passed as
  * kernel parameters (there is no other per-frame input). */

@@ -154,3 +154,24 @@ extern "C" void bh8_harness_atan2f(const float* y, const float* x, int n, float*
 extern "C" void bh8_harness_sincos(const double* x, int n, double* s, double* c) {
   for (int i = 0; i < n; ++i) bh8::sincos_(x[i], &s[i], &c[i]);
 }
+
+// Scripted animation: the code bh8_animate_kernel runs per entity, on the host.
+#include <vector>
+
+#include "bh8_anim.cuh"
+
+extern "C" int bh8_harness_replay(const bh8_scene* scene0, const bh8_basis* basis, const bh8_camera* cam0,
+                                  const bh8_action* actions, int n_actions, int n_frames, bh8_camera* cams,
+                                  bh8_object* objs, char* err) {
+  const int n_obj = scene0->n_obj;
+  std::vector<Bh8Action> acts(n_actions + 1);
+  if (const char* why = bh8a_prepare_actions(actions, n_actions, n_obj, acts.data())) {
+    std::strcpy(err, why);
+    return BH8_EINVAL;
+  }
+  std::vector<Bh8Entity> ent(n_obj + 1);
+  bh8a_prepare_entities(scene0, basis, cam0, ent.data());
+  for (int me = 0; me <= n_obj; ++me)
+    bh8a_replay_entity(ent[me], me, n_obj, acts.data(), n_actions, n_frames, scene0->obj, cam0, cams, objs);
+  return BH8_OK;
+}
