@@ -388,6 +388,41 @@ def measure_sink(r, my_frames, W, H, world=1, rank=0, frames=120, quality=95):
             "host_opencv_imencode": out["cpu"]}
 
 
+def measure_script(r, seq, which, d_frame, flags=0):
+    """SURVEY 8f-3, reported beside the headline (N = 1): the frame sequence drawn from a device-resident
+    script (bh8_script_*: the reference's per-frame Move*/Rotate* calls replayed on the GPU, frame constants
+    built there, nothing per frame from the host) next to the same frames drawn from host snapshots
+    (bh8_render_device), both back to back on one stream, wall clock around a final sync."""
+    try:
+        from blackhole_8_b200 import abi
+        from blackhole_8_b200.renderer import Script
+        n = len(seq)
+        disc = [o.kind for o in seq[0].objects].index(abi.KIND_ANNULUS)
+        t0 = time.perf_counter()
+        sc = Script(r, seq[0], abi.reference_script(which, n, disc), n, flags=flags)
+        create_s = time.perf_counter() - t0
+        cam, objs = sc.state(n - 1)
+        same = (list(cam.pos) == list(seq[n - 1].camera.pos) and
+                all([list(a) for a in o.v] == [list(a) for a in q.v] for o, q in zip(objs, seq[n - 1].objects)))
+        out = {}
+        for name, draw in (("script", lambda k: sc.render(k, d_frame)),
+                           ("host_snapshots", lambda k: r.render_device(seq[k], d_frame, flags=flags))):
+            for k in range(10):
+                draw(k)
+            r.sync()
+            t0 = time.perf_counter()
+            for k in range(n):
+                draw(k)
+            r.sync()
+            out[name] = n / (time.perf_counter() - t0)
+        sc.close()
+        return {"what": "bh8_script_render: %d frames of '%s' animated and set up on the GPU, no per-frame host data"
+                        % (n, which), "frames_per_s": out["script"], "host_snapshot_frames_per_s": out["host_snapshots"],
+                "create_ms": create_s * 1e3, "last_state_equals_reference": bool(same)}
+    except Exception as e:  # an extra: never fail the headline line over it
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -564,6 +599,9 @@ def main():
     frame_ok = bool(pinned[0].array[0, :, :, 3].min() == 255 and pinned[1].array[0, :, :, 3].min() == 255)
 
     sink = measure_sink(r, my_frames, W, H, world, rank)  # every rank: one sink per GPU
+    script = None
+    if world == 1 and args.workload in ("cfg1_spin", "cfg3_flythrough"):
+        script = measure_script(r, seq, args.workload, ring, flags)
 
     if rank != 0:
         if world > 1:
@@ -642,6 +680,8 @@ def main():
     }
     if sink:
         line["sink"] = sink
+    if script:
+        line["script"] = script
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

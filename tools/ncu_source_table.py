@@ -43,6 +43,31 @@ def main():
         b[1] += a[1]
     for f, b in sorted(byfile.items(), key=lambda kv: -kv[1][0]):
         print("  %-20s %9.1f instr/warp  %5.1f%% of samples" % (f, b[0] / warps, 100.0 * b[1] / max(1, samples)))
+    # per enclosing function (same crude ranges as tools/sass_static_table.py)
+    import os
+    import re
+    src_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "blackhole_8_b200", "csrc")
+    ranges = {}
+    for fn in ("bh8_ray.cuh", "bh8_kernel.cuh"):
+        out = []
+        for n, text in enumerate(open(os.path.join(src_dir, fn)), 1):
+            m = re.match(r"\s*(?:BH8_HD|__global__|__device__|static __device__|inline)\b.*?\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text)
+            if m and not text.strip().startswith("//"):
+                out.append((n, m.group(1)))
+        ranges[fn] = out
+    byfn = {}
+    for (f, line), a in agg.items():
+        name = f
+        for first, fn in ranges.get(f, []):
+            if first <= line:
+                name = f + ":" + fn
+        b = byfn.setdefault(name, [0, 0])
+        b[0] += a[0]
+        b[1] += a[1]
+    print("by function:")
+    for f, b in sorted(byfn.items(), key=lambda kv: -kv[1][0])[:30]:
+        print("  %-40s %9.1f instr/warp  %5.1f%% of samples" % (f, b[0] / warps, 100.0 * b[1] / max(1, samples)))
+    print("by line:")
     for (f, line), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top_n]:
         print("%s:%-4d %9.1f %5.1f%%  %s" % (f, line, a[0] / warps, 100.0 * a[1] / max(1, samples), a[2]))
 
