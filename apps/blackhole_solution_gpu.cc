@@ -6,7 +6,9 @@
 // CUDA renderer.  Headless: runs a scripted number of frames instead of reading keys.
 //
 //   blackhole_solution_gpu [--cfg N] [--width W] [--height H] [--frames K] [--nstep S]
-//                          [--texdir DIR] [--out PREFIX] [--video FILE.avi]
+//                          [--texdir DIR] [--out PREFIX] [--video FILE.avi] [--script]
+// --script: the frame loop's tail (camera script + disc spin) is recorded as a blackhole::gpu::Script and
+// replayed on the GPU; frames are drawn from the device-resident script instead of host snapshots.
 // Writes PREFIX_<frame>.bgr (raw: int32 rows, int32 cols, BGR bytes) when --out is given, and a
 // Motion-JPEG AVI (the reference's video.avi, :71-72; frames encoded on the GPU) when --video is.
 #include <chrono>
@@ -22,6 +24,7 @@
 int main(int argc, char** argv) {
   int cfg = 0, width = 960, height = 540, frames = 1, nstep = -1;
   std::string texdir = "build/textures", out, video;
+  bool scripted = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -33,6 +36,7 @@ int main(int argc, char** argv) {
     else if (a == "--texdir") texdir = next();
     else if (a == "--out") out = next();
     else if (a == "--video") video = next();
+    else if (a == "--script") scripted = true;
     else {
       std::fprintf(stderr, "unknown argument %s\n", a.c_str());
       return 2;
@@ -51,6 +55,34 @@ int main(int argc, char** argv) {
     std::unique_ptr<blackhole::gpu::VideoWriter> out_capture;
     if (!video.empty()) out_capture.reset(new blackhole::gpu::VideoWriter(&gpu, video, width, height, 29));
     cv::Mat screen;
+    if (scripted) {  // the same loop tail, written down once and replayed on the device
+      if (!scene->disc) throw std::runtime_error("--script needs a scene with the accretion disc");
+      blackhole::gpu::Script fly(&gpu);
+      int disc_key = -1;
+      manager.ForEach([&](int key, const blackhole::DrawableObject<bh8scenes::value_type>& obj) {
+        if (&obj == scene->disc) disc_key = key;
+      });
+      for (int k = 0; k + 1 < frames; ++k) {
+        if (cfg == 3) {
+          if (k < 120) {
+            fly.Camera(k, BH8_OP_MOVE_X, 10);
+          } else {
+            fly.Camera(k, BH8_OP_ROTATE_Z, blackhole::pi / 1800.0 * 10);
+            fly.Camera(k, BH8_OP_MOVE_Y, 10);
+          }
+        }
+        fly.Object(k, disc_key, BH8_OP_ROTATE_Z, blackhole::pi / 180);
+      }
+      fly.Compile(manager, *scene->blackhole, scene->camera, frames, nstep);
+      for (int k = 0; k < frames; ++k) {
+        fly.Render(k, &screen);
+        if (!out.empty()) cv::imwrite(out + "_" + std::to_string(k), screen);
+      }
+      const bh8_camera last = fly.CameraAt(frames - 1);
+      std::cout << "script: " << frames << " frames, camera ends at (" << last.pos[0] << ", " << last.pos[1] << ", "
+                << last.pos[2] << ")\n";
+      return 0;
+    }
     for (int k = 0; k < frames; ++k) {
       const auto t1 = std::chrono::high_resolution_clock::now();
       if (out_capture) out_capture->Write(manager, *scene->blackhole, scene->camera, nstep);

@@ -92,6 +92,106 @@ class Renderer {
   bh8_stats stats_{};
   std::vector<const unsigned char*> uploaded_;
   friend class VideoWriter;
+  friend class Script;
+};
+
+// A scripted animation: the Move* / Rotate* calls the reference's frame loop makes after
+// each frame (key handlers and the disc spin, blackhole_solution_test.cc:346-407), written down and
+// replayed ON THE GPU -- bit-identical to calling them on the live objects -- so that a long
+// fly-through needs no per-frame host work at all:
+//
+//   blackhole::gpu::Script fly(&gpu);
+//   for (int k = 0; k + 1 < frames; ++k) {
+//     fly.Camera(k, BH8_OP_MOVE_X, 10);                          // camera.MoveX(10) after frame k
+//     fly.Object(k, id_acc_disc.first, BH8_OP_ROTATE_Z, pi / 180);  // id_acc_disc.second->RotateZ(pi/180)
+//   }
+//   fly.Compile(manager, blackhole, camera, frames);             // state now = frame 0
+//   fly.Render(k, &screen);
+class Script {
+ public:
+  explicit Script(Renderer* gpu) : gpu_(gpu) {}
+  ~Script() { Reset(); }
+  Script(const Script&) = delete;
+  Script& operator=(const Script&) = delete;
+
+  // After frame `frame` is drawn: camera.<op>(amount).  Calls must be recorded in frame order.
+  void Camera(int frame, int op, double amount) { actions_.push_back(Make(frame, BH8_TARGET_CAMERA, op, amount)); }
+  // After frame `frame` is drawn: the object with this ObjectManager key .<op>(amount).
+  void Object(int frame, int key, int op, double amount) { actions_.push_back(Make(frame, -2 - key, op, amount)); }
+
+  template <typename T>
+  void Compile(const ObjectManager<T>& manager, const StaticBlackhole<T>& blackhole, const ::blackhole::Camera<T>& camera,
+               int n_frames, int nstep = 20) {
+    Reset();
+    const SceneSnapshot snap = Snapshot(manager, blackhole);
+    const bh8_camera cam = Snapshot(camera);
+    gpu_->UploadTextures(snap);
+    std::vector<bh8_basis> basis;
+    manager.ForEach([&](int, const DrawableObject<T>& obj) {
+      bh8_basis b{};
+      detail::Put3(b.vx, obj.vector_x());
+      detail::Put3(b.vy, obj.vector_y());
+      detail::Put3(b.vz, obj.vector_z());
+      basis.push_back(b);
+    });
+    std::vector<bh8_action> acts = actions_;
+    for (bh8_action& a : acts) {
+      if (a.target == BH8_TARGET_CAMERA) continue;
+      const int key = -2 - a.target;
+      a.target = -2;
+      for (size_t j = 0; j < snap.objects.size(); ++j)
+        if (snap.objects[j].key == key) a.target = static_cast<int>(j);
+      if (a.target < 0) throw std::runtime_error("Script: no object with key " + std::to_string(key));
+    }
+    const bh8_scene scene = snap.view();
+    bh8_params prm{};
+    prm.nstep = nstep;
+    prm.pixel_format = BH8_PIXEL_BGR8;
+    width_ = cam.width;
+    height_ = cam.height;
+    gpu_->Check(bh8_script_create(gpu_->ctx_, &scene, basis.data(), &cam, &prm, acts.data(), static_cast<int>(acts.size()),
+                                  n_frames, &script_));
+    gpu_->Check(bh8_frame_alloc(gpu_->ctx_, static_cast<size_t>(width_) * height_ * 3, &d_frame_));
+  }
+
+  int frames() const { return bh8_script_frames(script_); }
+
+  // Frame `frame` into a CV_8UC3 (BGR) cv::Mat, like Renderer::Render.
+  void Render(int frame, cv::Mat* out) {
+    if (!script_) throw std::runtime_error("Script::Render before Compile");
+    if (out->empty() || out->rows != height_ || out->cols != width_ || out->type() != CV_8UC3)
+      *out = cv::Mat(height_, width_, CV_8UC3);
+    gpu_->Check(bh8_script_render(script_, frame, d_frame_, nullptr, nullptr, nullptr));
+    gpu_->Check(bh8_memcpy_d2h(gpu_->ctx_, out->data, d_frame_, static_cast<size_t>(width_) * height_ * 3));
+  }
+
+  // The camera / objects of frame `frame` as the device replay left them (for checks and HUD text).
+  bh8_camera CameraAt(int frame) {
+    bh8_camera cam{};
+    gpu_->Check(bh8_script_state(script_, frame, &cam, nullptr));
+    return cam;
+  }
+
+ private:
+  static bh8_action Make(int frame, int target, int op, double amount) {
+    bh8_action a{};
+    a.frame = frame;
+    a.target = target;
+    a.op = op;
+    a.amount = amount;
+    return a;
+  }
+  void Reset() {
+    if (d_frame_) bh8_frame_free(gpu_->ctx_, d_frame_);
+    if (script_) bh8_script_destroy(script_);
+    d_frame_ = nullptr;
+    script_ = nullptr;
+  }
+  Renderer* gpu_;
+  std::vector<bh8_action> actions_;
+  bh8_script* script_ = nullptr;
+  void* d_frame_ = nullptr;
+  int width_ = 0, height_ = 0;
 };
 
 // Stands where the reference's cv::VideoWriter out_capture(save_dir/"video.avi",
@@ -122,6 +222,33 @@ class VideoWriter {
     prm.nstep = nstep;
     if (bh8_sink_render(sink_, &scene, &cam, &prm) != BH8_OK)
       throw std::runtime_error(std::string("bh8_sink_render: ") + bh8_sink_last_error(sink_));
+  }
+
+  // Pipelined Write(): returns once the frame is queued; frame k+1 is traced while frame k is encoded.
+  template <typename T>
+  void WriteAsync(const ObjectManager<T>& manager, const StaticBlackhole<T>& blackhole, const Camera<T>& camera,
+                  int nstep = 20) {
+    const SceneSnapshot snap = Snapshot(manager, blackhole);
+    const bh8_camera cam = Snapshot(camera);
+    gpu_->UploadTextures(snap);
+    const bh8_scene scene = snap.view();
+    bh8_params prm{};
+    prm.nstep = nstep;
+    if (bh8_sink_submit(sink_, &scene, &cam, &prm) != BH8_OK)
+      throw std::runtime_error(std::string("bh8_sink_submit: ") + bh8_sink_last_error(sink_));
+  }
+  void Flush() {
+    if (bh8_sink_flush(sink_) != BH8_OK) throw std::runtime_error(std::string("bh8_sink_flush: ") + bh8_sink_last_error(sink_));
+  }
+
+  // One video from the per-GPU files of a frame-sharded job, frames back in order (host only).
+  static unsigned long long Merge(const std::vector<std::string>& parts, const std::string& out_path) {
+    std::vector<const char*> p;
+    for (const std::string& s : parts) p.push_back(s.c_str());
+    uint64_t frames = 0, bytes = 0;
+    if (bh8_sink_merge(p.data(), static_cast<int>(p.size()), out_path.c_str(), &frames, &bytes) != BH8_OK)
+      throw std::runtime_error(std::string("bh8_sink_merge: ") + bh8_last_error(nullptr));
+    return frames;
   }
 
   // Finishes the file (index, sizes); returns its size in bytes.

@@ -121,3 +121,19 @@ def test_gpu_driver_app_matches_reference_frame(textures, tmp_path):
     f7 = np.fromfile(prefix + "_7.bgr", dtype=np.uint8)[8:].reshape(540, 960, 3)
     diff = np.abs(f7.astype(int) - ref7["bgr"].astype(int)).max(2)
     assert (diff > parity.RGB_TOL).mean() < 0.002
+
+
+@pytest.mark.gpu
+def test_gpu_driver_app_scripted_frames_equal_host_replayed_frames(textures, tmp_path):
+    """apps/blackhole_solution_gpu --script (blackhole::gpu::Script: the loop tail replayed on the GPU) must
+    write exactly the frames the same driver writes when it moves the live objects on the host."""
+    exe = os.path.join(BUILD, "blackhole_solution_gpu")
+    assert os.path.exists(exe), "built by test_gpu_driver_app_matches_reference_frame"
+    common = ["--cfg", "3", "--width", "480", "--height", "270", "--frames", "130", "--texdir", textures]
+    host, dev = str(tmp_path / "h"), str(tmp_path / "d")
+    subprocess.run([exe] + common + ["--out", host], check=True, stdout=subprocess.DEVNULL)
+    out = subprocess.run([exe] + common + ["--out", dev, "--script"], check=True, capture_output=True, text=True).stdout
+    assert "script: 130 frames" in out
+    for k in (0, 1, 60, 119, 120, 121, 129):
+        a, b = open("%s_%d.bgr" % (host, k), "rb").read(), open("%s_%d.bgr" % (dev, k), "rb").read()
+        assert a == b, "frame %d differs" % k
