@@ -38,6 +38,29 @@ FLOPS_SETUP = 385
 FLOPS_TERMINAL = 130
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result.  Libraries write there too (NCCL prints its
+    version banner on stdout at init), so file descriptor 1 is pointed at stderr for the whole run and
+    the result goes to the saved descriptor, unbuffered, the moment it exists."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def load_snapshot(name=WORKLOAD):
     from blackhole_8_b200 import abi
     return abi.SceneSnapshot.from_json(os.path.join(ROOT, "tests", "golden", name + ".json"))
@@ -215,7 +238,7 @@ def bench_reference(args, rank, world):
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def bench_8k_stripes(args, r, base, rank, world, flags):
@@ -290,7 +313,7 @@ def bench_8k_stripes(args, r, base, rank, world, flags):
     peak, _ = r.measure_fp64_peak()
     n_extra = max(0, base.scene.n_obj - 2)
     flops = (FLOPS_PER_STEP_BASE + FLOPS_PER_EXTRA_OBJECT * n_extra) * cnt[1].item() + FLOPS_SETUP * cnt[0].item()
-    print(json.dumps({
+    emit(({
         "metric": "Mrays/s", "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": steps,
         "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -436,6 +459,7 @@ def main():
                     help="frame sequence: configs[1] with the disc spinning frame to frame as in the "
                          "reference's loop (default), the configs[3] fly-through, or configs[1] frame 0 only")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -581,15 +605,20 @@ def main():
         r.wait(r.submit(my_frames[i], pinned[i & 1].array, flags=flags))
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    prev = None
-    for i in range(e2e_steps):
-        tk = r.submit(my_frames[args.warmup + i], pinned[i & 1].array, flags=flags)
-        if prev is not None:
-            r.wait(prev)
-        prev = tk
-    r.wait(prev)
-    e2e_s = time.perf_counter() - t0
+    # three passes over the same e2e_steps frames, the median pass counts (a pass lasts tens of ms, so
+    # a single one is at the mercy of one scheduling hiccup on the host)
+    passes = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        prev = None
+        for i in range(e2e_steps):
+            tk = r.submit(my_frames[args.warmup + i], pinned[i & 1].array, flags=flags)
+            if prev is not None:
+                r.wait(prev)
+            prev = tk
+        r.wait(prev)
+        passes.append(time.perf_counter() - t0)
+    e2e_s = sorted(passes)[1]
     if world > 1:
         t = torch.tensor([e2e_s, sync_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -671,7 +700,9 @@ def main():
                 "host_placement": ("rank 0 bound to %d CPUs next to its GPU (NVML affinity), every rank likewise"
                                    % len(numa_cpus)) if numa_cpus else "as launched",
                 "what": "bh8_submit()/bh8_wait(): snapshot -> kernel parameters, RGBA8 frame read back into pinned "
-                        "host memory, two frames in flight (copy of frame k overlaps kernel of frame k+1), wall clock",
+                        "host memory, two frames in flight, each on its own stream (copy of frame k and the tail of its kernel "
+                        "overlap kernel k+1), wall clock, median of 3 passes over the same frames",
+                "passes_s": passes,
                 "synchronous_bh8_render": {"value": e2e_sync_value, "unit": "Mrays/s",
                                            "frames_per_s": world * e2e_steps / sync_s}},
         "gpu_launches": launches,
@@ -682,7 +713,7 @@ def main():
         line["sink"] = sink
     if script:
         line["script"] = script
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
