@@ -19,7 +19,7 @@
 #include <string>
 
 #include "blackhole/gpu/renderer.h"
-#include "scenes.h"  // oracle/scenes.h: the BASELINE scenes, written against the public header API
+#include "scenes.h"  // apps/scenes.h: the BASELINE scenes, written against the public header API
 
 int main(int argc, char** argv) {
   int cfg = 0, width = 960, height = 540, frames = 1, nstep = -1;

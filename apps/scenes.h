@@ -1,6 +1,8 @@
 // scenes.h -- the BASELINE.json configurations, built through the blackhole:: header API.
 //
-// TEST INFRASTRUCTURE (oracle side) and demo-scene source for the GPU driver.  This file only
+// Scene source of the GPU driver (apps/blackhole_solution_gpu.cc); the oracle's restatement
+// (oracle/ref_render.cc) builds the SAME scenes from it through the reference's own headers.  It is not
+// part of the oracle and contains no rendering code.  This file only
 // uses the public API that lackhole/blackhole_8 ships in include/blackhole/ (Camera,
 // ObjectManager, Annulus, Rectangle, InfinitePlane, ChessPattern2D, StaticBlackhole), so it
 // compiles unchanged against EITHER the reference's own headers (-I/root/reference/include, used

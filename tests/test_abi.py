@@ -52,8 +52,12 @@ def test_no_cpu_fallback_without_a_device(lib):
 
 
 def test_product_package_does_not_touch_the_oracle():
-    pkg = os.path.join(ROOT, "blackhole_8_b200")
-    for dirpath, _, files in os.walk(pkg):
+    """Neither the package, nor the public headers, nor the driver apps may import, include, link or load
+    anything under oracle/ (only tests/, smoke() and bench.py's CPU-baseline legs do)."""
+    walk = []
+    for top in ("blackhole_8_b200", "include", "apps"):
+        walk += list(os.walk(os.path.join(ROOT, top)))
+    for dirpath, _, files in walk:
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                 text = open(os.path.join(dirpath, f)).read()

@@ -39,7 +39,7 @@ def textures():
 @pytest.fixture(scope="module")
 def own_render(textures):
     exe = os.path.join(BUILD, "own_render")
-    subprocess.run(CXX + ["-fopenmp", "-I" + os.path.join(ROOT, "oracle"),
+    subprocess.run(CXX + ["-fopenmp", "-I" + os.path.join(ROOT, "oracle"), "-I" + os.path.join(ROOT, "apps"),
                           os.path.join(ROOT, "oracle", "ref_render.cc"), "-o", exe], check=True)
     return exe
 
@@ -86,7 +86,7 @@ def test_gpu_driver_app_matches_reference_frame(textures, tmp_path):
     build()
     exe = os.path.join(BUILD, "blackhole_solution_gpu")
     subprocess.run(["g++", "-std=gnu++17", "-O2", "-DNDEBUG", "-I" + os.path.join(ROOT, "third_party", "cvshim"),
-                    "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle"),
+                    "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "apps"),
                     os.path.join(ROOT, "apps", "blackhole_solution_gpu.cc"), "-o", exe,
                     "-L" + os.path.join(ROOT, "blackhole_8_b200"), "-lbh8",
                     "-Wl,-rpath," + os.path.join(ROOT, "blackhole_8_b200")], check=True)

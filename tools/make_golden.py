@@ -35,7 +35,7 @@ SMALL = {
     "cfg3_frame180_480x270": (3, 480, 270, 180, None),
     "cfg4_nstep200_320x180": (4, 320, 180, 0, None),
     "cfg1_odd_333x187": (1, 333, 187, 0, None),  # ragged size: not a multiple of any tile
-    # stress scenes (oracle/scenes.h cfg 6-9): the GPU path's rarely taken branches
+    # stress scenes (apps/scenes.h cfg 6-9): the GPU path's rarely taken branches
     "cfg6_offplane_400x225": (6, 400, 225, 0, None),
     "cfg7_lookaway_400x225": (7, 400, 225, 0, None),
     "cfg8_manyplanes_400x225": (8, 400, 225, 0, None),
