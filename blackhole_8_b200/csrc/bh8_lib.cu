@@ -55,6 +55,7 @@ struct bh8_ctx {
   uint64_t launches = 0;
   uint64_t next_ticket = 0;  // bh8_submit
   bool submit_slot_streams = true;  // $BH8_SUBMIT_ONE_STREAM=1: kernels on one stream, copies on another (A/B knob)
+  int resolve_wait = 0x7fffffff;    // $BH8_RESOLVE_WAIT: tuning knob for the batching window, read once at creation
   std::vector<void*> owned;  // bh8_frame_alloc results (device 0)
 };
 
@@ -119,7 +120,7 @@ int launch_frame(bh8_ctx* ctx, Device& d, const bh8_scene* scene, const bh8_came
   out.vec_ok = (f.width % 4 == 0) && (reinterpret_cast<uintptr_t>(d_pixels) % 16 == 0) &&
                f.pixel_format != BH8_PIXEL_BGR8;
   BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
-  if (const char* w = std::getenv("BH8_RESOLVE_WAIT")) f.resolve_wait = std::atoi(w);  // tuning knob
+  if (ctx->resolve_wait != 0x7fffffff) f.resolve_wait = ctx->resolve_wait;  // tuning knob
   if (prm->flags & BH8_FLAG_NO_BATCHING) f.resolve_wait = -1;  // exact tests run at once
   // One instantiation per number of non-central planes with an FP32 side filter; scenes with more
   // planes than filter slots take the generic instantiation (exact test on every gated step).
@@ -209,6 +210,7 @@ int bh8_create(bh8_ctx** out, const int* devices, int n_dev) {
   if (!ctx) return fail(nullptr, BH8_ENOMEM, "out of host memory");
   ctx->n_dev = n_dev;
   if (const char* one = std::getenv("BH8_SUBMIT_ONE_STREAM")) ctx->submit_slot_streams = std::atoi(one) == 0;
+  if (const char* w = std::getenv("BH8_RESOLVE_WAIT")) ctx->resolve_wait = std::atoi(w);
   for (int i = 0; i < n_dev; ++i) {
     Device& d = ctx->dev[i];
     d.ordinal = devices ? devices[i] : i;

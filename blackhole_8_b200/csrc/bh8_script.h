@@ -117,8 +117,7 @@ int bh8_script_create(bh8_ctx* ctx, const bh8_scene* scene0, const bh8_basis* ob
       ts.rows[i] = ctx->tex_rows[i];
       ts.cols[i] = ctx->tex_cols[i];
     }
-    int resolve_wait = 0x7fffffff;
-    if (const char* w = std::getenv("BH8_RESOLVE_WAIT")) resolve_wait = std::atoi(w);  // tuning knob, as launch_frame
+    const int resolve_wait = ctx->resolve_wait;  // tuning knob, as launch_frame
     if (e == cudaSuccess) {
       bh8::bh8_build_frames_kernel<<<(n_frames + 63) / 64, 64, 0, d.stream>>>(
           s->d_cams, s->d_objs, n_obj, s->bh_index, s->prm, ts, resolve_wait, s->d_frames, d_status, n_frames);
