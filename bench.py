@@ -454,6 +454,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batching", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true",
+                    help="tuning runs: skip the e2e / sink / script / CPU legs (their keys are null; not a driver line)")
     ap.add_argument("--workload", default="cfg1_spin",
                     choices=["cfg1_spin", "cfg3_flythrough", "cfg1_static", "cfg10_flat", "cfg4_8k"],
                     help="frame sequence: configs[1] with the disc spinning frame to frame as in the "
@@ -583,6 +585,15 @@ def main():
     ms_per_step = kernel_ms / args.steps
     total_rays = rays * world * args.steps
     value = total_rays / (kernel_ms * 1e-3) / 1e6
+    if args.kernel_only:  # tuning aid, not the driver's line
+        if rank == 0:
+            emit({"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+                  "ms_per_step": ms_per_step, "kernel_only": True, "clocks": clocks, "gpu_launches": launches,
+                  "lib": os.environ.get("BH8_LIB_PATH", "default")})
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the public host-buffer calls --------------------------------------------
     # (a) bh8_render: one synchronous call per frame.  (b) bh8_submit / bh8_wait: the streaming form

@@ -31,6 +31,11 @@ constexpr int kTileW = 32;
 #endif
 constexpr int kTileH = BH8_TILE_H;
 constexpr int kThreads = kTileW * kTileH;
+#ifndef BH8_PATCH_W
+#define BH8_PATCH_W 8  // a warp is a BH8_PATCH_W x (32 / BH8_PATCH_W) pixel patch (measured: 8x4 best of 4x8, 8x4, 16x2)
+#endif
+constexpr int kPatchW = BH8_PATCH_W, kPatchH = 32 / BH8_PATCH_W, kPatchesAcross = kTileW / kPatchW;
+static_assert(kPatchW * kPatchH == 32 && kTileH % kPatchH == 0, "a warp must tile the CTA's pixels");
 constexpr int kMaxFilterPlanes = kMaxFilterSlots;
 #ifndef BH8_UPDATES_PER_VOTE
 #define BH8_UPDATES_PER_VOTE 2  // geodesic updates between two rounds of warp votes
@@ -197,9 +202,9 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
   }
   if (y0 >= f.height) return;
 
-  // warp = 8x4 patch; slot = row-major position in the 32x8 tile
-  const int px = (warp & 3) * 8 + (lane & 7);
-  const int py = (warp >> 2) * 4 + (lane >> 3);
+  // warp = kPatchW x kPatchH patch (8x4); slot = row-major position in the 32x8 tile
+  const int px = (warp % kPatchesAcross) * kPatchW + (lane % kPatchW);
+  const int py = (warp / kPatchesAcross) * kPatchH + (lane / kPatchW);
   const int slot = py * kTileW + px;
   const int x = x0 + px, y = y0 + py;
   const bool inside = x < f.width && y < f.height;
@@ -301,8 +306,8 @@ __device__ __forceinline__ void linear_tile(const Bh8Frame& f, const Bh8Tex& tex
     y0 = blockIdx.y * kTileH;
   }
   if (y0 >= f.height) return;
-  const int px = (warp & 3) * 8 + (lane & 7);
-  const int py = (warp >> 2) * 4 + (lane >> 3);
+  const int px = (warp % kPatchesAcross) * kPatchW + (lane % kPatchW);
+  const int py = (warp / kPatchesAcross) * kPatchH + (lane / kPatchW);
   const int slot = py * kTileW + px;
   const int x = x0 + px, y = y0 + py;
   const bool inside = x < f.width && y < f.height;
