@@ -43,6 +43,23 @@ def _worker(rank, world, port, mode, out_path):
                     for r0, r1 in sharding.stripe_rows_of(h, 16, r, world):
                         frame[r0:r1] = b[r0:r1]
                 np.save(out_path, frame.numpy())
+        elif mode == "video":
+            # one sink per rank on its own frames (the GPU ranks encode with nvJPEG; here cv2 stands in),
+            # then rank 0 merges the per-rank files into ONE video in frame order (bh8_sink_merge)
+            import cv2
+            from blackhole_8_b200.renderer import VideoSink, merge_video_parts
+            base = np.ascontiguousarray(O.load_golden("cfg1_odd_333x187")["bgr"])
+            h, w = base.shape[:2]
+            n_frames = 7
+            part = out_path + ".part%d.avi" % rank
+            with VideoSink(None, part, w, h, fps=29) as sink:
+                for k in sharding.frames_of(n_frames, rank, world):
+                    ok, enc = cv2.imencode(".jpg", np.roll(base, 9 * k, axis=1), [cv2.IMWRITE_JPEG_QUALITY, 95])
+                    sink.append_jpeg(enc.tobytes())
+            dist.barrier()
+            if rank == 0:
+                frames, _ = merge_video_parts([out_path + ".part%d.avi" % r for r in range(world)], out_path)
+                assert frames == n_frames
         else:
             names = ["cfg3_frame60_480x270", "cfg3_frame180_480x270", "cfg5_480x270"]
             frames = []
@@ -70,6 +87,24 @@ def test_frames_dealt_round_robin_cover_the_flythrough(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), "frames", out), nprocs=2, join=True)
     names = ["cfg3_frame60_480x270", "cfg3_frame180_480x270", "cfg5_480x270"]
     assert list(np.load(out)) == [O.load_golden(n)["digest"]["bgr"] for n in names]
+
+
+def test_per_rank_videos_merge_into_one_file_in_frame_order(tmp_path):
+    import cv2
+    out = str(tmp_path / "video.avi")
+    mp.spawn(_worker, args=(2, _free_port(), "video", out), nprocs=2, join=True)
+    base = np.ascontiguousarray(O.load_golden("cfg1_odd_333x187")["bgr"])
+    cap = cv2.VideoCapture(out)
+    k = 0
+    while True:
+        ok, frame = cap.read()
+        if not ok:
+            break
+        want = np.roll(base, 9 * k, axis=1)
+        mse = np.mean((frame.astype(float) - want.astype(float)) ** 2)
+        assert 10 * np.log10(255.0 ** 2 / mse) > 30.0, "frame %d is not frame %d of the job" % (k, k)
+        k += 1
+    assert k == 7
 
 
 def test_partitions_are_disjoint_covers():
