@@ -49,6 +49,24 @@ class Renderer {
     Check(bh8_render(ctx_, &scene, &cam, 1, &prm, frame->data, nullptr, nullptr, nullptr, &stats_));
   }
 
+  // Flat space: the pixel loop of ray_tracer_test.cc:140-155 -- RayTracer(camera.focus(), PixelVector)
+  // with BasicLinearRayRecurrence, Prograde(manager, dst, steps) (ray_tracer.h:17-35,68-85) and the
+  // colour of the hit -- for the whole frame in one call.
+  template <typename T>
+  void RenderLinear(const ObjectManager<T>& manager, const Camera<T>& camera, cv::Mat* frame, int steps = 10) {
+    const SceneSnapshot snap = SnapshotFlat(manager);
+    const bh8_camera cam = Snapshot(camera);
+    UploadTextures(snap);
+    if (frame->empty() || frame->rows != cam.height || frame->cols != cam.width || frame->type() != CV_8UC3)
+      *frame = cv::Mat(cam.height, cam.width, CV_8UC3);
+    const bh8_scene scene = snap.view();
+    bh8_params prm{};
+    prm.tracer = BH8_TRACER_LINEAR;
+    prm.linear_steps = steps;
+    prm.pixel_format = BH8_PIXEL_BGR8;
+    Check(bh8_render(ctx_, &scene, &cam, 1, &prm, frame->data, nullptr, nullptr, nullptr, &stats_));
+  }
+
   // A fly-through: one snapshot per frame (the host replays Camera / Object moves between
   // snapshots, object.h:58-88), rendered in one call; frames are dealt to the context's devices.
   void RenderFrames(const std::vector<SceneSnapshot>& scenes, const std::vector<bh8_camera>& cameras,

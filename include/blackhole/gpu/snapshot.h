@@ -54,7 +54,7 @@ bh8_camera Snapshot(const Camera<T>& camera) {
 // next to the manager, blackhole_solution_test.cc:148).  Textures are shared, not copied
 // (cv::Mat reference counting); slots are assigned per distinct pixel buffer.
 template <typename T>
-SceneSnapshot Snapshot(const ObjectManager<T>& manager, const StaticBlackhole<T>& blackhole) {
+SceneSnapshot Snapshot(const ObjectManager<T>& manager, const StaticBlackhole<T>* blackhole_ptr) {
   SceneSnapshot snap;
   if (manager.size() > BH8_MAX_OBJECTS) throw std::runtime_error("scene has more than BH8_MAX_OBJECTS objects");
   manager.ForEach([&](int key, const DrawableObject<T>& obj) {
@@ -79,7 +79,7 @@ SceneSnapshot Snapshot(const ObjectManager<T>& manager, const StaticBlackhole<T>
       case ShapeKind::kBlackhole:
         o.kind = BH8_KIND_BLACKHOLE;
         o.mass = static_cast<const StaticBlackhole<T>&>(obj).mass();
-        if (&obj == &blackhole) snap.bh_index = static_cast<int>(snap.objects.size());
+        if (&obj == blackhole_ptr) snap.bh_index = static_cast<int>(snap.objects.size());
         break;
       case ShapeKind::kAnnulus: {
         const auto& disc = static_cast<const Annulus<T>&>(obj);
@@ -116,8 +116,20 @@ SceneSnapshot Snapshot(const ObjectManager<T>& manager, const StaticBlackhole<T>
     }
     snap.objects.push_back(o);
   });
-  if (snap.bh_index < 0) throw std::runtime_error("the black hole is not an object of this ObjectManager");
+  if (blackhole_ptr && snap.bh_index < 0)
+    throw std::runtime_error("the black hole is not an object of this ObjectManager");
   return snap;
+}
+
+template <typename T>
+SceneSnapshot Snapshot(const ObjectManager<T>& manager, const StaticBlackhole<T>& blackhole) {
+  return Snapshot(manager, &blackhole);
+}
+
+// A flat-space scene (ray_tracer_test.cc: no hole the rays bend around; bh_index = -1).
+template <typename T>
+SceneSnapshot SnapshotFlat(const ObjectManager<T>& manager) {
+  return Snapshot(manager, static_cast<const StaticBlackhole<T>*>(nullptr));
 }
 
 }  // namespace gpu

@@ -137,3 +137,26 @@ def test_gpu_driver_app_scripted_frames_equal_host_replayed_frames(textures, tmp
     for k in (0, 1, 60, 119, 120, 121, 129):
         a, b = open("%s_%d.bgr" % (host, k), "rb").read(), open("%s_%d.bgr" % (dev, k), "rb").read()
         assert a == b, "frame %d differs" % k
+
+
+@pytest.mark.gpu
+def test_gpu_flat_space_driver_matches_the_reference_frames(textures, tmp_path):
+    """apps/ray_tracer_gpu: the ray_tracer_test.cc scene and its "Movement test" through the header API, the
+    pixel loop (:140-155) replaced by Renderer::RenderLinear.  Frame 0 and frame 25 against the frames the
+    reference's own RayTracer class drew (tests/golden cfg10_*)."""
+    exe = os.path.join(BUILD, "ray_tracer_gpu")
+    subprocess.run(["g++", "-std=gnu++17", "-O2", "-DNDEBUG", "-I" + os.path.join(ROOT, "third_party", "cvshim"),
+                    "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "apps"),
+                    os.path.join(ROOT, "apps", "ray_tracer_gpu.cc"), "-o", exe,
+                    "-L" + os.path.join(ROOT, "blackhole_8_b200"), "-lbh8",
+                    "-Wl,-rpath," + os.path.join(ROOT, "blackhole_8_b200")], check=True)
+    for name, w, h, frame in (("cfg10_flat_800x450", 800, 450, 0), ("cfg10_flat_frame25_640x360", 640, 360, 25)):
+        prefix = str(tmp_path / name)
+        out = subprocess.run([exe, "--width", str(w), "--height", str(h), "--frames", str(frame + 1), "--texdir",
+                              textures, "--out", prefix], check=True, capture_output=True, text=True).stdout
+        assert out.count("Took") == frame + 1
+        g = O.load_golden(name)
+        got = np.fromfile("%s_%d.bgr" % (prefix, frame), dtype=np.uint8)[8:].reshape(h, w, 3)
+        hit_ok = (got.sum(2) > 0) == (g["bgr"].sum(2) > 0)
+        diff = np.abs(got.astype(int) - g["bgr"].astype(int)).max(2)
+        assert hit_ok.mean() > 0.999 and (diff > parity.RGB_TOL).mean() < parity.RGB_OUTLIER_MAX, name
