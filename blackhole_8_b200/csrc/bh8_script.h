@@ -17,6 +17,11 @@ struct bh8_script {
   bh8_camera* d_cams = nullptr;
   bh8_object* d_objs = nullptr;
   std::vector<int> n_nc;  // per frame: which instantiation of the render kernel it takes
+  // bh8_script_render_range: the captured launch sequence of the last range drawn
+  cudaGraphExec_t graph = nullptr;
+  int g_first = -1, g_count = 0;
+  void* g_base = nullptr;
+  size_t g_stride = 0;
 };
 
 namespace {
@@ -30,6 +35,7 @@ void script_free(bh8_script* s) {
   if (!s) return;
   if (s->ctx && cudaSetDevice(s->ctx->dev[0].ordinal) == cudaSuccess) {
     cudaStreamSynchronize(s->ctx->dev[0].stream);
+    if (s->graph) cudaGraphExecDestroy(s->graph);
     cudaFree(s->d_frames);
     cudaFree(s->d_cams);
     cudaFree(s->d_objs);
@@ -196,6 +202,54 @@ int bh8_script_render(bh8_script* s, int frame, void* d_pixels, void* d_class, v
   }
   BH8_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
+  return BH8_OK;
+}
+
+int bh8_script_render_range(bh8_script* s, int first, int count, void* d_base, size_t frame_stride_bytes) {
+  if (!s) return BH8_EINVAL;
+  bh8_ctx* ctx = s->ctx;
+  if (first < 0 || count < 1 || first + count > s->n_frames)
+    return fail(ctx, BH8_EINVAL, "bh8_script_render_range: frames out of range");
+  const size_t frame_bytes = static_cast<size_t>(s->width) * s->height * bh8_pixel_bytes(s->prm.pixel_format);
+  if (!d_base || frame_stride_bytes < frame_bytes)
+    return fail(ctx, BH8_EINVAL, "bh8_script_render_range: null buffer or stride smaller than a frame");
+  Device& d = ctx->dev[0];
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  if (!s->graph || s->g_first != first || s->g_count != count || s->g_base != d_base || s->g_stride != frame_stride_bytes) {
+    if (s->graph) {
+      BH8_CUDA(ctx, cudaStreamSynchronize(d.stream));
+      cudaGraphExecDestroy(s->graph);
+      s->graph = nullptr;
+    }
+    // Capture what `count` bh8_script_render() calls enqueue -- constants to the symbol, kernel, next
+    // frame -- into one graph: the whole range then costs the host a single launch.
+    const uint64_t launches_before = ctx->launches;
+    BH8_CUDA(ctx, cudaStreamBeginCapture(d.stream, cudaStreamCaptureModeThreadLocal));
+    int rc = BH8_OK;
+    for (int k = 0; k < count && rc == BH8_OK; ++k)
+      rc = bh8_script_render(s, first + k, static_cast<uint8_t*>(d_base) + static_cast<size_t>(k) * frame_stride_bytes,
+                             nullptr, nullptr, nullptr);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(d.stream, &graph);
+    ctx->launches = launches_before;  // nothing ran yet
+    if (rc != BH8_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (ce != cudaSuccess) return fail(ctx, BH8_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&s->graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      s->graph = nullptr;
+      return fail(ctx, BH8_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+    }
+    s->g_first = first;
+    s->g_count = count;
+    s->g_base = d_base;
+    s->g_stride = frame_stride_bytes;
+  }
+  BH8_CUDA(ctx, cudaGraphLaunch(s->graph, d.stream));
+  ctx->launches += static_cast<uint64_t>(count);
   return BH8_OK;
 }
 

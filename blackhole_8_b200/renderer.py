@@ -68,6 +68,7 @@ def load_library(path=None):
                                     C.POINTER(abi.Params), C.POINTER(abi.Action), i32, i32, C.POINTER(vp)]),
         "bh8_script_frames": (i32, [vp]),
         "bh8_script_render": (i32, [vp, i32, vp, vp, vp, vp]),
+        "bh8_script_render_range": (i32, [vp, i32, i32, vp, C.c_size_t]),
         "bh8_script_state": (i32, [vp, i32, C.POINTER(abi.Camera), C.POINTER(abi.Object)]),
         "bh8_script_frame_constants": (i32, [vp, i32, vp, C.c_size_t]),
         "bh8_host_frame_constants": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params),
@@ -308,6 +309,10 @@ class Script:
     def render(self, frame, d_pixels, d_cls=None, d_key=None, d_steps=None):
         self._r._check(self.lib.bh8_script_render(self._h, frame, C.c_void_p(d_pixels), C.c_void_p(d_cls),
                                                   C.c_void_p(d_key), C.c_void_p(d_steps)))
+
+    def render_range(self, first, count, d_base, frame_stride_bytes):
+        """Frames first .. first+count-1 into d_base + i * stride with ONE host launch (a CUDA graph)."""
+        self._r._check(self.lib.bh8_script_render_range(self._h, first, count, C.c_void_p(d_base), frame_stride_bytes))
 
     def state(self, frame):
         """(abi.Camera, [abi.Object]) of frame `frame`, read back from the device."""

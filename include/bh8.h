@@ -303,6 +303,11 @@ int bh8_script_frames(const bh8_script* script);
 /* Draw frame `frame` into device buffers (as bh8_render_device; d_class / d_key / d_steps nullable).
  * Asynchronous on the context's stream; bh8_sync() waits. */
 int bh8_script_render(bh8_script* script, int frame, void* d_pixels, void* d_class, void* d_key, void* d_steps);
+/* Draw frames first .. first + count - 1 into d_base + i * frame_stride_bytes (device memory; the stride
+ * is at least one frame, so frames do not overlap).  The launch sequence is captured once into a CUDA
+ * graph (and re-used while the arguments stay the same), so the whole range costs the host ONE launch.
+ * Asynchronous on the context's stream. */
+int bh8_script_render_range(bh8_script* script, int first, int count, void* d_base, size_t frame_stride_bytes);
 /* Read frame `frame`'s snapshot back: cam (nullable) and objs (nullable, n_obj entries). */
 int bh8_script_state(bh8_script* script, int frame, bh8_camera* cam, bh8_object* objs);
 /* Verification hook: the device-built frame constants of frame `frame` (bytes = bh8_frame_bytes()) and

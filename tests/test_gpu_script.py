@@ -130,3 +130,39 @@ def test_script_errors():
         sc.render(1, buf)
         r.sync()
         r.frame_free(buf)
+
+
+def test_graph_captured_range_draws_the_same_frames():
+    """bh8_script_render_range: 12 frames with one host launch (CUDA graph) == 12 bh8_script_render calls;
+    a second launch re-uses the graph, a different range rebuilds it."""
+    from gpu_util import renderer
+    snap0, frames = load_states("cfg3_flythrough")
+    snap0 = snap0.with_resolution(320, 180)
+    h, w = 180, 320
+    r = renderer()
+    r.set_textures(snap0, O.load_texture)
+    acts = abi.reference_script("cfg3_flythrough", 140, disc_index(snap0))
+    fb = h * w * 4
+    with Script(r, snap0, acts, 140) as sc:
+        one = r.frame_alloc(fb)
+        many = r.frame_alloc(12 * fb)
+        for first in (0, 118, 118, 3):
+            launches = r.launches
+            r.memset_d(many, 0, 12 * fb)
+            sc.render_range(first, 12, many, fb)
+            r.sync()
+            assert r.launches - launches == 12
+            got = np.empty((12, h, w, 4), np.uint8)
+            r.memcpy_d2h(got, many)
+            for k in range(12):
+                sc.render(first + k, one)
+                r.sync()
+                ref = np.empty((h, w, 4), np.uint8)
+                r.memcpy_d2h(ref, one)
+                assert np.array_equal(got[k], ref), (first, k)
+        with pytest.raises(Bh8Error, match="out of range"):
+            sc.render_range(130, 12, many, fb)
+        with pytest.raises(Bh8Error, match="stride"):
+            sc.render_range(0, 2, many, fb - 4)
+        r.frame_free(one)
+        r.frame_free(many)
