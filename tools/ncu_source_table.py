@@ -3,7 +3,12 @@
 
 usage: ncu -i X.ncu-rep --page source --csv --print-source cuda,sass > src.csv
        python tools/ncu_source_table.py src.csv <warps_launched> [top_n]
-Prints executed warp instructions per launched warp and stall samples, by file and by line."""
+Prints executed warp instructions per launched warp and stall samples, by file and by line.
+
+NOTE: ncu lists an inlined instruction under every source file of its call chain, so the per-file and
+per-function sums here count such instructions more than once (the total comes out ~15 % high for this
+kernel).  For instruction budgets use tools/ncu_function_table.py, which counts every SASS address once
+and attributes it to its innermost source line; this tool stays for the per-line stall samples."""
 import csv
 import sys
 
