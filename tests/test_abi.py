@@ -64,3 +64,19 @@ def test_product_package_does_not_touch_the_oracle():
                 bad = re.findall(r"import\s+\S*oracle|from\s+\S*oracle|libbh8_oracle|bh8_oracle_|"
                                  r"#include\s+\"[^\"]*oracle|CDLL\([^)]*oracle", text)
                 assert not bad, (os.path.join(dirpath, f), bad)
+
+
+def test_header_is_plain_c_and_struct_sizes_match_the_ctypes_mirror(tmp_path):
+    """include/bh8.h must be consumable by a C compiler (the boundary is a C ABI, not a C++ one) and the
+    ctypes mirror of every POD must have the size the C compiler gives it."""
+    import subprocess
+    src = tmp_path / "abi_sizes.c"
+    src.write_text('#include <stdio.h>\n#include "bh8.h"\nint main(void) {\n'
+                   '  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(bh8_camera), sizeof(bh8_object), sizeof(bh8_scene),\n'
+                   '         sizeof(bh8_params), sizeof(bh8_stats), sizeof(bh8_action), sizeof(bh8_basis));\n  return 0;\n}\n')
+    exe = tmp_path / "abi_sizes"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    mirror = [C.sizeof(t) for t in (abi.Camera, abi.Object, abi.Scene, abi.Params, abi.Stats, abi.Action, abi.Basis)]
+    assert sizes == mirror
