@@ -147,6 +147,7 @@ typedef struct bh8_ctx bh8_ctx;
 /* Create a context driving n_dev CUDA devices (devices[i] = ordinal; NULL = {0..n_dev-1}).
  * With n_dev > 1 peer access to devices[0] is enabled and frames are gathered there. */
 int bh8_create(bh8_ctx** out, const int* devices, int n_dev);
+/* Sinks and scripts opened on the context use its device, streams and textures: close them first. */
 void bh8_destroy(bh8_ctx* ctx);
 const char* bh8_last_error(const bh8_ctx* ctx); /* ctx may be NULL: error of the failed bh8_create */
 int bh8_abi_version(void);
