@@ -233,3 +233,23 @@ def test_pipelined_submit_writes_the_same_file_as_the_synchronous_sink(tmp_path)
             sink.submit(s)
         # close() appends what is still in flight
     assert open(pipe_path, "rb").read() == open(sync_path, "rb").read()
+
+
+@pytest.mark.gpu
+def test_flythrough_video_app_writes_one_readable_file(tmp_path):
+    """apps/flythrough_video.py (configs[3] end to end: per-GPU sinks + merge), single GPU, small frames,
+    once from host snapshots and once from a device-side script: same frame count, both readable."""
+    import json
+    import subprocess
+    import sys
+    app = os.path.join(O.ROOT, "apps", "flythrough_video.py")
+    for extra in ([], ["--script"]):
+        out = str(tmp_path / ("video%d.avi" % len(extra)))
+        res = subprocess.run([sys.executable, app, "--out", out, "--frames", "9", "--width", "320", "--height", "180"] + extra,
+                             check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+        line = json.loads(res)
+        assert line["frames"] == 9 and line["frames_read_back"] == 9
+        assert line["min_psnr_db_checked_frames"] > PSNR_MIN_DB - 4.0   # small, busy frames
+        info, frames = read_avi(out)
+        assert len(frames) == 9 and (info["w"], info["h"]) == (320, 180)
+        assert not any(p.endswith(".avi") and ".part" in p for p in os.listdir(tmp_path))
