@@ -80,16 +80,27 @@ def test_reference_programs_compile_unchanged_against_own_headers(textures, tmp_
         assert open(mine, "rb").read() == open(theirs, "rb").read(), t
 
 
-@pytest.mark.gpu
-def test_gpu_driver_app_matches_reference_frame(textures, tmp_path):
+def build_gpu_app(name):
+    """Compile apps/<name>.cc against the public headers and link it with the in-tree libbh8.so."""
     from blackhole_8_b200.build import build
     build()
-    exe = os.path.join(BUILD, "blackhole_solution_gpu")
+    exe = os.path.join(BUILD, name)
     subprocess.run(["g++", "-std=gnu++17", "-O2", "-DNDEBUG", "-I" + os.path.join(ROOT, "third_party", "cvshim"),
                     "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "apps"),
-                    os.path.join(ROOT, "apps", "blackhole_solution_gpu.cc"), "-o", exe,
+                    os.path.join(ROOT, "apps", name + ".cc"), "-o", exe,
                     "-L" + os.path.join(ROOT, "blackhole_8_b200"), "-lbh8",
                     "-Wl,-rpath," + os.path.join(ROOT, "blackhole_8_b200")], check=True)
+    return exe
+
+
+@pytest.fixture(scope="module")
+def solution_app():
+    return build_gpu_app("blackhole_solution_gpu")
+
+
+@pytest.mark.gpu
+def test_gpu_driver_app_matches_reference_frame(textures, tmp_path, solution_app):
+    exe = solution_app
     prefix = str(tmp_path / "f")
     video = str(tmp_path / "video.avi")
     out = subprocess.run([exe, "--cfg", "0", "--width", "960", "--height", "540", "--frames", "8", "--texdir",
@@ -124,11 +135,10 @@ def test_gpu_driver_app_matches_reference_frame(textures, tmp_path):
 
 
 @pytest.mark.gpu
-def test_gpu_driver_app_scripted_frames_equal_host_replayed_frames(textures, tmp_path):
+def test_gpu_driver_app_scripted_frames_equal_host_replayed_frames(textures, tmp_path, solution_app):
     """apps/blackhole_solution_gpu --script (blackhole::gpu::Script: the loop tail replayed on the GPU) must
     write exactly the frames the same driver writes when it moves the live objects on the host."""
-    exe = os.path.join(BUILD, "blackhole_solution_gpu")
-    assert os.path.exists(exe), "built by test_gpu_driver_app_matches_reference_frame"
+    exe = solution_app
     common = ["--cfg", "3", "--width", "480", "--height", "270", "--frames", "130", "--texdir", textures]
     host, dev = str(tmp_path / "h"), str(tmp_path / "d")
     subprocess.run([exe] + common + ["--out", host], check=True, stdout=subprocess.DEVNULL)
@@ -144,12 +154,7 @@ def test_gpu_flat_space_driver_matches_the_reference_frames(textures, tmp_path):
     """apps/ray_tracer_gpu: the ray_tracer_test.cc scene and its "Movement test" through the header API, the
     pixel loop (:140-155) replaced by Renderer::RenderLinear.  Frame 0 and frame 25 against the frames the
     reference's own RayTracer class drew (tests/golden cfg10_*)."""
-    exe = os.path.join(BUILD, "ray_tracer_gpu")
-    subprocess.run(["g++", "-std=gnu++17", "-O2", "-DNDEBUG", "-I" + os.path.join(ROOT, "third_party", "cvshim"),
-                    "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "apps"),
-                    os.path.join(ROOT, "apps", "ray_tracer_gpu.cc"), "-o", exe,
-                    "-L" + os.path.join(ROOT, "blackhole_8_b200"), "-lbh8",
-                    "-Wl,-rpath," + os.path.join(ROOT, "blackhole_8_b200")], check=True)
+    exe = build_gpu_app("ray_tracer_gpu")
     for name, w, h, frame in (("cfg10_flat_800x450", 800, 450, 0), ("cfg10_flat_frame25_640x360", 640, 360, 25)):
         prefix = str(tmp_path / name)
         out = subprocess.run([exe, "--width", str(w), "--height", str(h), "--frames", str(frame + 1), "--texdir",
