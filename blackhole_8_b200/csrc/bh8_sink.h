@@ -165,7 +165,7 @@ class AviMjpgReader {
     }
     std::fseek(fp_, 0, SEEK_END);
     const long file_end = std::ftell(fp_);
-    if (!walk(12, file_end, err)) return false;
+    if (!walk(12, file_end, 0, err)) return false;
     if (width_ <= 0 || height_ <= 0 || !(fps_ > 0)) {
       *err = std::string(path) + ": no avih / strh header found";
       return false;
@@ -197,7 +197,11 @@ class AviMjpgReader {
     *v = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
     return true;
   }
-  bool walk(long at, long end, std::string* err) {
+  bool walk(long at, long end, int depth, std::string* err) {
+    if (depth > 8) {  // AVI nests LISTs two deep; a crafted file must not recurse without bound
+      *err = "LIST chunks nested too deeply in an AVI part";
+      return false;
+    }
     while (at + 8 <= end) {
       std::fseek(fp_, at, SEEK_SET);
       char id[4];
@@ -211,7 +215,7 @@ class AviMjpgReader {
       if (std::memcmp(id, "LIST", 4) == 0) {
         char kind[4];
         if (!tag(kind)) break;
-        if (!walk(body + 4, body + (long)size, err)) return false;
+        if (!walk(body + 4, body + (long)size, depth + 1, err)) return false;
       } else if (std::memcmp(id, "avih", 4) == 0 && size >= 40) {
         uint32_t v[10];
         for (int i = 0; i < 10; ++i) u32(&v[i]);

@@ -253,3 +253,44 @@ def test_flythrough_video_app_writes_one_readable_file(tmp_path):
         info, frames = read_avi(out)
         assert len(frames) == 9 and (info["w"], info["h"]) == (320, 180)
         assert not any(p.endswith(".avi") and ".part" in p for p in os.listdir(tmp_path))
+
+
+def test_merge_survives_damaged_parts(tmp_path):
+    """Truncated, bit-flipped and size-corrupted part files are either merged (if still well-formed) or rejected
+    with an error -- never a crash; deeply nested LIST chunks are refused."""
+    import struct as st
+    from blackhole_8_b200.renderer import merge_video_parts
+    f = np.zeros((48, 64, 3), np.uint8)
+    f[10:30, 20:40] = 200
+    good = str(tmp_path / "good.avi")
+    with VideoSink(None, good, 64, 48) as s:
+        for _ in range(5):
+            s.append_jpeg(_jpeg(f))
+    raw = open(good, "rb").read()
+    rng = np.random.default_rng(1)
+    bad, out = str(tmp_path / "bad.avi"), str(tmp_path / "out.avi")
+    outcomes = {"merged": 0, "rejected": 0}
+    for it in range(600):
+        b = bytearray(raw)
+        if it % 3 == 0:
+            b = b[:int(rng.integers(0, len(b)))]
+        elif it % 3 == 1:
+            for _ in range(int(rng.integers(1, 8))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        else:
+            i = int(rng.integers(0, len(b) - 4))
+            b[i:i + 4] = int(rng.integers(0, 2 ** 32)).to_bytes(4, "little")
+        open(bad, "wb").write(bytes(b))
+        try:
+            merge_video_parts([bad], out)
+            outcomes["merged"] += 1
+        except Bh8Error:
+            outcomes["rejected"] += 1
+    assert outcomes["merged"] > 0 and outcomes["rejected"] > 0
+    depth = 5000  # RIFF AVI + LIST(LIST(LIST(...)))
+    body = b""
+    for _ in range(depth):
+        body = b"LIST" + st.pack("<I", len(body) + 4) + b"movi" + body
+    open(bad, "wb").write(b"RIFF" + st.pack("<I", len(body) + 4) + b"AVI " + body)
+    with pytest.raises(Bh8Error, match="nested"):
+        merge_video_parts([bad], out)
