@@ -59,3 +59,52 @@ def test_gpu_matches_oracle_on_random_scenes(seed):
     ref = O.render(snap)
     got = gpu_render(snap, stats=False)
     print(seed, check(got, ref, "seed %d" % seed))
+
+
+def test_damaged_snapshots_never_hang_the_ray_code():
+    """NaN, infinities, zeros and huge values anywhere in a snapshot: the per-ray state machine (the code the
+    kernel's lanes run) must still terminate for every pixel -- on the GPU a lane that never ends would hang
+    the frame.  The frames themselves are meaningless; only termination (and a clean error for snapshots the
+    frame builder rejects) is asserted."""
+    import signal
+    from blackhole_8_b200 import abi
+    from test_ray_math_host import harness_render
+    special = [float("nan"), float("inf"), -float("inf"), 0.0, -0.0, 1e300, -1e300, 1e-300, 5e-324, 1e18, -1e18]
+    rng = np.random.default_rng(7)
+
+    class Hang(Exception):
+        pass
+
+    def on_alarm(sig, frame):
+        raise Hang()
+
+    old = signal.signal(signal.SIGALRM, on_alarm)
+    rendered = rejected = 0
+    try:
+        for it in range(300):
+            d = random_snapshot(int(rng.integers(0, 100)), 16, 9).to_dict()
+            for _ in range(int(rng.integers(1, 4))):
+                v = special[int(rng.integers(0, len(special)))]
+                where = int(rng.integers(0, 3))
+                if where == 0:
+                    d["camera"][["pos", "vx", "vy", "vz"][int(rng.integers(0, 4))]][int(rng.integers(0, 3))] = v
+                elif where == 1:
+                    d["camera"]["focus_len"] = v
+                else:
+                    o = d["objects"][int(rng.integers(0, len(d["objects"])))]
+                    f = ["v", "n", "ex", "ey", "r_in", "r_out", "mass", "pattern_size"][int(rng.integers(0, 8))]
+                    if isinstance(o[f], list):
+                        o[f][int(rng.integers(0, len(o[f])))] = v
+                    else:
+                        o[f] = v
+            signal.alarm(30)
+            try:
+                harness_render(abi.SceneSnapshot.from_dict(d))
+                rendered += 1
+            except AssertionError:  # bh8_build_frame said no (mass <= 0, zero normal, ...)
+                rejected += 1
+            finally:
+                signal.alarm(0)
+    finally:
+        signal.signal(signal.SIGALRM, old)
+    assert rendered > 200 and rejected > 0
