@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include "bh8_ray.cuh"
+#include "bh8_warp.cuh"
 
 namespace bh8 {
 
@@ -64,61 +65,6 @@ struct DeviceFetch {
     return (uint32_t)t.x | ((uint32_t)t.y << 8) | ((uint32_t)t.z << 16);
   }
 };
-
-// Register budget.  The stepping loop needs ~40 registers, the exact segment test ~110.  Letting the
-// second set the kernel's register count would halve the occupancy, so (a) everything only the rare
-// paths use lives in the ray's mailbox in shared memory to begin with (bh8::Mail), and (b) a lane
-// that enters the exact test first parks the few stepping values it holds in registers and
-// re-loads them afterwards: no stepping value is live inside the test, and the test is entered
-// about once per ray.  (volatile: the compiler must not forward the stores to the loads, which
-// would keep the values alive in registers.)
-// Mailbox, stride kThreads: bh8::Mail's slots, then doubles u, phi, dphi_prev, binv2 and ints i,
-// state, lo of a parked lane (binv2 and lo are written once: a frozen lane always has its base lo).
-constexpr int kMailDoubles = kMailDoublesRay + 4;
-constexpr int kMailInts = kMailIntsRay + 3;
-enum : int { kKdU = kMailDoublesRay, kKdPhi, kKdDphi, kKdBinv2 };
-enum : int { kKwI = kMailIntsRay, kKwState, kKwLo };
-
-template <int NN>
-__device__ __forceinline__ void lane_park_constants(const Lane<NN>& L, const Mail m) {
-  m.set_d(kKdBinv2, L.binv2);
-  m.set_w(kKwLo, L.lo);
-}
-
-// What a frozen lane still carries in registers and the exact test needs or changes.
-template <int NN>
-__device__ __forceinline__ void lane_park(const Lane<NN>& L, const Mail m) {
-  m.set_d(kKdU, L.u);
-  m.set_d(kKdPhi, L.phi);
-  m.set_d(kKdDphi, L.dphi_prev);
-  m.set_w(kKwI, L.idx());
-  m.set_w(kKwState, L.state);
-}
-
-// Re-load a lane from its mailbox: frozen (as lane_freeze leaves it) or, if the exact test cleared
-// the segment (state kRun), travelling again with the values the test left in Mail's slots.
-template <int NN>
-__device__ __forceinline__ void lane_unpark(Lane<NN>& L, const Mail m) {
-  L.u = m.get_d(kKdU);
-  L.phi = m.get_d(kKdPhi);
-  L.dphi_prev = m.get_d(kKdDphi);
-  L.binv2 = m.get_d(kKdBinv2);
-  L.state = m.get_w(kKwState);
-  L.lo = m.get_w(kKwLo);
-  L.set_idx(m.get_w(kKwI));
-  L.bgr = 0;
-  L.oob = 0;
-  if (L.state == kRun) {
-    lane_thaw(L, m);
-  } else {
-    L.delta = 0.0;
-    L.du_h = 0.0;
-    L.trig_hi = kTrigNever;
-    L.t_thr = kTrigNever;
-    L.span = 0xffffffffu;
-    L.inc = 0;
-  }
-}
 
 // Pixel store + optional maps + optional counters, shared by both kernels.  RGBA8 / BGRA8 go through
 // a shared tile and leave as 16-byte coalesced stores (4 pixels per store, 128 B per tile row).
@@ -235,27 +181,10 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
 #pragma unroll
     for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k) lane_update(f, L, mail);
     const unsigned present = __reduce_or_sync(0xffffffffu, (unsigned)L.state);
-    const unsigned runs = present & kRun, pend = present & (kPend | kPendChord);
-    if (pend == 0u) {
-      if (runs == 0u) break;  // every ray of the patch has ended
-      continue;
-    }
-    // Parked exact tests wait for company: until no lane is stepping any more or the oldest has
-    // waited resolve_wait rounds; then all of them run together.
-    if (runs != 0u && ++waited <= f.resolve_wait) continue;
-    waited = 0;
-    if (L.state & (kPend | kPendChord)) {
-      lane_park(L, mail);
-      {
-        Lane<NN> T;  // the test works on its own copy, loaded from the mailbox
-        lane_unpark(T, mail);
-        lane_exact(f, T, mail);
-        if (T.state == kPendChord) lane_exact(f, T, mail);  // event right after a cleared segment
-        if (T.state == kRun) lane_freeze(T, mail, kRun);    // hand the thawed values over through Mail
-        lane_park(T, mail);
-      }
-      lane_unpark(L, mail);
-    }
+    const int todo = warp_decide(present, waited, f.resolve_wait);
+    if (todo == kWarpStep) continue;
+    if (todo == kWarpDone) break;  // every ray of the patch has ended
+    if (L.state & (kPend | kPendChord)) lane_resolve(f, L, mail);
   }
   const int steps = inside ? mail.get_w(kMwSteps) : 0;
   const int hit_obj = inside ? mail.get_w(kMwHit) : -1;

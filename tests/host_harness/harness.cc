@@ -11,6 +11,7 @@
 #define BH8_HOST_COUNTERS 1
 static unsigned long long bh8_host_filter_evaluations = 0;  // bumped by side_filter()
 #include "bh8_ray.cuh"
+#include "bh8_warp.cuh"
 
 extern "C" unsigned long long bh8_harness_take_filter_evaluations() {
   const unsigned long long n = bh8_host_filter_evaluations;
@@ -173,5 +174,100 @@ extern "C" int bh8_harness_replay(const bh8_scene* scene0, const bh8_basis* basi
   bh8a_prepare_entities(scene0, basis, cam0, ent.data());
   for (int me = 0; me <= n_obj; ++me)
     bh8a_replay_entity(ent[me], me, n_obj, acts.data(), n_actions, n_frames, scene0->obj, cam0, cams, objs);
+  return BH8_OK;
+}
+
+// ---- a warp of the kernel, emulated ---------------------------------------------------------------
+// 32 lanes = one 8x4-pixel patch, stepped in lockstep exactly as render_tile (bh8_kernel.cuh) does it:
+// `updates_per_vote` straight-line updates for EVERY lane (frozen and dead ones included), the OR of
+// the lanes' states, bh8::warp_decide, and bh8::lane_resolve (park -> exact test on a copy -> unpark)
+// for the parked lanes -- the same functions the kernel inlines, with a mailbox laid out as in shared
+// memory (component c of lane l at [c * 32 + l]).  What the per-lane loop above cannot show -- lanes
+// waiting frozen while others travel, batched tests, the register parking -- is exercised here.
+template <int NN>
+static void trace_frame_warps(const Bh8Frame& f, const HostFetch& fetch, int updates_per_vote, uint8_t* out_bgr,
+                              uint8_t* out_class, int8_t* out_key, uint16_t* out_steps, uint64_t* counters) {
+  constexpr int kLanes = 32, kPW = 8, kPH = 4;
+  for (int py0 = 0; py0 < f.height; py0 += kPH) {
+    for (int px0 = 0; px0 < f.width; px0 += kPW) {
+      double md[bh8::kMailDoubles * kLanes];
+      int32_t mw[bh8::kMailInts * kLanes];
+      bh8::Lane<NN> L[kLanes];
+      bh8::Mail mail[kLanes];
+      bool inside[kLanes];
+      for (int l = 0; l < kLanes; ++l) {
+        mail[l] = bh8::Mail{md + l, mw + l, kLanes};
+        const int x = px0 + (l % kPW), y = py0 + (l / kPW);
+        inside[l] = x < f.width && y < f.height;
+        bh8::lane_inert(L[l]);
+        if (inside[l]) {
+          bh8::lane_setup(f, x, y, L[l], mail[l]);
+          bh8::lane_park_constants(L[l], mail[l]);
+        }
+      }
+      int waited = 0;
+      for (uint64_t round = 0;; ++round) {
+        unsigned present = 0;
+        for (int l = 0; l < kLanes; ++l) {
+          for (int k = 0; k < updates_per_vote; ++k) bh8::lane_update(f, L[l], mail[l]);
+          present |= (unsigned)L[l].state;
+        }
+        counters[0] += (uint64_t)updates_per_vote;  // update slots of this warp
+        const int todo = bh8::warp_decide(present, waited, f.resolve_wait);
+        if (todo == bh8::kWarpStep) continue;
+        if (todo == bh8::kWarpDone) break;
+        counters[1]++;  // resolve passes
+        for (int l = 0; l < kLanes; ++l)
+          if (L[l].state & (bh8::kPend | bh8::kPendChord)) bh8::lane_resolve(f, L[l], mail[l]);
+        if (round > 100000000ull) return;  // a warp that never ends would hang the GPU: leave zeros, the test fails
+      }
+      for (int l = 0; l < kLanes; ++l) {
+        if (!inside[l]) continue;
+        const int x = px0 + (l % kPW), y = py0 + (l / kPW);
+        const int hit_obj = mail[l].get_w(bh8::kMwHit);
+        bh8::lane_shade(f, L[l], mail[l], hit_obj, fetch);
+        const uint32_t bgr = L[l].bgr;
+        const size_t i = static_cast<size_t>(y) * f.width + x;
+        out_bgr[3 * i] = bgr & 255;
+        out_bgr[3 * i + 1] = (bgr >> 8) & 255;
+        out_bgr[3 * i + 2] = (bgr >> 16) & 255;
+        out_class[i] = (uint8_t)(hit_obj >= 0 ? f.obj[hit_obj].cls : BH8_CLASS_BACKGROUND);
+        out_key[i] = (int8_t)(hit_obj >= 0 ? f.obj[hit_obj].key : -1);
+        out_steps[i] = (uint16_t)mail[l].get_w(bh8::kMwSteps);
+      }
+    }
+  }
+}
+
+// counters[0] = update slots summed over warps (each slot = one update of all 32 lanes), counters[1] =
+// resolve passes summed over warps.
+extern "C" int bh8_harness_render_warps(const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
+                                        const HarnessTexture* textures, int n_textures, int filter_slots,
+                                        int updates_per_vote, int resolve_wait, uint8_t* out_bgr, uint8_t* out_class,
+                                        int8_t* out_key, uint16_t* out_steps, uint64_t* counters, char* err) {
+  int rows[BH8_MAX_TEXTURES] = {0}, cols[BH8_MAX_TEXTURES] = {0};
+  for (int i = 0; i < n_textures && i < BH8_MAX_TEXTURES; ++i) {
+    rows[i] = textures[i].rows;
+    cols[i] = textures[i].cols;
+  }
+  Bh8Frame f;
+  const int rc = bh8_build_frame(scene, cam, prm, rows, cols, &f, err);
+  if (rc != BH8_OK) return rc;
+  if (f.tracer == BH8_TRACER_LINEAR) {
+    std::strcpy(err, "the warp emulation is for the geodesic kernel");
+    return BH8_EINVAL;
+  }
+  f.resolve_wait = resolve_wait;
+  const HostFetch fetch{textures};
+  counters[0] = counters[1] = 0;
+  const int u = updates_per_vote;
+  switch ((filter_slots >= 0 && f.n_nc <= 4) ? f.n_nc : -1) {
+    case 0: trace_frame_warps<0>(f, fetch, u, out_bgr, out_class, out_key, out_steps, counters); break;
+    case 1: trace_frame_warps<1>(f, fetch, u, out_bgr, out_class, out_key, out_steps, counters); break;
+    case 2: trace_frame_warps<2>(f, fetch, u, out_bgr, out_class, out_key, out_steps, counters); break;
+    case 3: trace_frame_warps<3>(f, fetch, u, out_bgr, out_class, out_key, out_steps, counters); break;
+    case 4: trace_frame_warps<4>(f, fetch, u, out_bgr, out_class, out_key, out_steps, counters); break;
+    default: trace_frame_warps<-1>(f, fetch, u, out_bgr, out_class, out_key, out_steps, counters); break;
+  }
   return BH8_OK;
 }

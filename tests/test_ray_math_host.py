@@ -61,6 +61,50 @@ def harness_render(snap, nstep=None, filter_slots=4):
     return out
 
 
+def harness_render_warps(snap, nstep=None, filter_slots=4, updates_per_vote=2, resolve_wait=2):
+    """The kernel's WARP schedule emulated on the CPU (32 lanes in lockstep, votes, batched exact tests with
+    register parking: bh8_warp.cuh, the code render_tile inlines)."""
+    L = harness()
+    h, w = snap.height, snap.width
+    texs = [O.load_texture(n) for n in snap.textures]
+    tarr = (HarnessTexture * max(1, len(texs)))()
+    for i, t in enumerate(texs):
+        tarr[i] = HarnessTexture(t.ctypes.data, t.shape[0], t.shape[1])
+    prm = snap.params(abi.PIXEL_BGR8, 0, nstep)
+    out = {"bgr": np.zeros((h, w, 3), np.uint8), "cls": np.zeros((h, w), np.uint8),
+           "key": np.zeros((h, w), np.int8), "steps": np.zeros((h, w), np.uint16)}
+    err = C.create_string_buffer(256)
+    counters = (C.c_uint64 * 2)()
+    rc = L.bh8_harness_render_warps(C.byref(snap.scene), C.byref(snap.camera), C.byref(prm), tarr, len(texs),
+                                    C.c_int(filter_slots), C.c_int(updates_per_vote), C.c_int(resolve_wait),
+                                    out["bgr"].ctypes.data_as(C.c_void_p), out["cls"].ctypes.data_as(C.c_void_p),
+                                    out["key"].ctypes.data_as(C.c_void_p), out["steps"].ctypes.data_as(C.c_void_p),
+                                    counters, err)
+    assert rc == 0, err.value
+    n_warps = ((h + 3) // 4) * ((w + 7) // 8)
+    out["update_slots_per_warp"] = counters[0] / n_warps
+    out["resolve_passes_per_warp"] = counters[1] / n_warps
+    return out
+
+
+@pytest.mark.parametrize("name", O.golden_names(full=False))
+def test_warp_schedule_draws_the_same_frames(name):
+    """Lanes that wait frozen while their neighbours travel, exact tests run in batches, stepping values
+    parked in the mailbox around the test: none of it may change a pixel, a hit key or a step count
+    against the one-lane-at-a-time run -- for the kernel's schedule and for other batching windows."""
+    g = O.load_golden(name)
+    if g["snap"].linear_steps > 0:
+        pytest.skip("flat-space scene: the linear kernel has no warp schedule")
+    one = harness_render(g["snap"])
+    for upv, wait in ((2, 2), (1, 0), (3, 5), (2, -1)):
+        got = harness_render_warps(g["snap"], updates_per_vote=upv, resolve_wait=wait)
+        for k in ("bgr", "cls", "key", "steps"):
+            assert np.array_equal(got[k], one[k]), (name, upv, wait, k)
+    got = harness_render_warps(g["snap"])
+    print(name, "update slots per warp %.1f (mean steps per ray %.1f), resolve passes per warp %.2f" %
+          (got["update_slots_per_warp"], one["steps"].mean(), got["resolve_passes_per_warp"]))
+
+
 @pytest.mark.parametrize("name", O.golden_names(full=False))
 def test_kernel_ray_math_matches_reference_frames(name):
     g = O.load_golden(name)

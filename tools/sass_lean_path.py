@@ -40,11 +40,12 @@ def main():
         t = ins[k][1]
         if "BRA.DIV" in t:  # taken only by a diverged warp
             return [k + 1]
-        m = re.search(r"\bBRA\b.*?(0x[0-9a-f]+)$", t)
+        m = re.search(r"\bBRA(?:\.U)?(?:\.ANY)?\b.*?(0x[0-9a-f]+)$", t)
         if m:
             tgt = index.get(int(m.group(1), 16))
             out = [tgt] if tgt is not None else []
-            if t.startswith("@"):
+            # conditional: a guard predicate (@P0 BRA) or a uniform-predicate operand (BRA.U !UP0, target)
+            if t.startswith("@") or re.search(r"BRA\.U(?:\.ANY)?\s+!?UP\d", t):
                 out.append(k + 1)
             return out
         if t.startswith("EXIT") or t.startswith("RET"):
