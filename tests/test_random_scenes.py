@@ -35,6 +35,15 @@ def test_host_compiled_kernel_code_matches_oracle_on_random_scenes(seed):
     print(seed, check(got, ref, "seed %d" % seed), "classes", np.bincount(ref["cls"].ravel(), minlength=4).tolist())
 
 
+@pytest.mark.parametrize("seed", SEEDS[:40])
+def test_emulated_warp_schedule_matches_oracle_on_random_scenes(seed):
+    """The same scenes through the kernel's warp schedule emulated on the CPU (tests/host_harness): lanes in
+    lockstep, batched exact tests, register parking."""
+    from test_ray_math_host import harness_render_warps
+    snap = random_snapshot(seed)
+    check(harness_render_warps(snap), O.render(snap), "seed %d (warp schedule)" % seed)
+
+
 def test_random_scenes_cover_every_class_and_both_plane_kinds():
     seen = np.zeros(4, int)
     central = noncentral = 0
