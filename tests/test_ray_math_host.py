@@ -23,22 +23,32 @@ class HarnessTexture(C.Structure):
     _fields_ = [("bgr", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32)]
 
 
-def harness():
+_VARIANTS = {}
+
+
+def harness(defines=()):
+    """The test-only host build of the kernel's per-ray code; `defines` selects a build variant
+    (e.g. ("BH8_ANNULUS_GATE=1",)), each in its own library."""
     global _LIB
-    if _LIB is None:
+    key = tuple(defines)
+    if key not in _VARIANTS:
         out = os.path.join(HERE, "host_harness", "_build")
         os.makedirs(out, exist_ok=True)
-        so = os.path.join(out, "libharness.so")
-        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off",
-                        "-I" + os.path.join(O.ROOT, "include"),
+        tag = "".join(c if c.isalnum() else "_" for c in "_".join(key))
+        so = os.path.join(out, "libharness%s.so" % (("_" + tag) if tag else ""))
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off"] +
+                       ["-D" + d for d in key] +
+                       ["-I" + os.path.join(O.ROOT, "include"),
                         "-I" + os.path.join(O.ROOT, "blackhole_8_b200", "csrc"),
                         os.path.join(HERE, "host_harness", "harness.cc"), "-o", so], check=True)
-        _LIB = C.CDLL(so)
-    return _LIB
+        _VARIANTS[key] = C.CDLL(so)
+    if not key:
+        _LIB = _VARIANTS[key]
+    return _VARIANTS[key]
 
 
-def harness_render(snap, nstep=None, filter_slots=4):
-    L = harness()
+def harness_render(snap, nstep=None, filter_slots=4, defines=()):
+    L = harness(defines)
     h, w = snap.height, snap.width
     texs = [O.load_texture(n) for n in snap.textures]
     tarr = (HarnessTexture * max(1, len(texs)))()
@@ -61,10 +71,10 @@ def harness_render(snap, nstep=None, filter_slots=4):
     return out
 
 
-def harness_render_warps(snap, nstep=None, filter_slots=4, updates_per_vote=2, resolve_wait=2):
+def harness_render_warps(snap, nstep=None, filter_slots=4, updates_per_vote=2, resolve_wait=2, defines=()):
     """The kernel's WARP schedule emulated on the CPU (32 lanes in lockstep, votes, batched exact tests with
     register parking: bh8_warp.cuh, the code render_tile inlines)."""
-    L = harness()
+    L = harness(defines)
     h, w = snap.height, snap.width
     texs = [O.load_texture(n) for n in snap.textures]
     tarr = (HarnessTexture * max(1, len(texs)))()
