@@ -6,7 +6,8 @@
 // CUDA renderer.  Headless: runs a scripted number of frames instead of reading keys.
 //
 //   blackhole_solution_gpu [--cfg N] [--width W] [--height H] [--frames K] [--nstep S]
-//                          [--texdir DIR] [--out PREFIX] [--video FILE.avi] [--script]
+//                          [--texdir DIR] [--out PREFIX] [--video FILE.avi] [--script] [--hud]
+// --hud: the reference's HUD text (:309-326) is drawn into the frames written with --out.
 // --script: the frame loop's tail (camera script + disc spin) is recorded as a blackhole::gpu::Script and
 // replayed on the GPU; frames are drawn from the device-resident script instead of host snapshots.
 // Writes PREFIX_<frame>.bgr (raw: int32 rows, int32 cols, BGR bytes) when --out is given, and a
@@ -24,7 +25,7 @@
 int main(int argc, char** argv) {
   int cfg = 0, width = 960, height = 540, frames = 1, nstep = -1;
   std::string texdir = "build/textures", out, video;
-  bool scripted = false;
+  bool scripted = false, hud = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -37,6 +38,7 @@ int main(int argc, char** argv) {
     else if (a == "--out") out = next();
     else if (a == "--video") video = next();
     else if (a == "--script") scripted = true;
+    else if (a == "--hud") hud = true;
     else {
       std::fprintf(stderr, "unknown argument %s\n", a.c_str());
       return 2;
@@ -91,6 +93,7 @@ int main(int argc, char** argv) {
       const auto us = std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();
       std::cout << "Took " << us / 1000.0 << "ms (kernel " << gpu.last_stats().kernel_ms << "ms, "
                 << gpu.last_stats().steps << " geodesic steps)\n";
+      if (hud && !out.empty()) blackhole::gpu::DrawHud(scene->camera, &screen);  // :309-326
       if (!out.empty()) cv::imwrite(out + "_" + std::to_string(k), screen);
       // frame loop tail, blackhole_solution_test.cc:346-407: fly-through script + disc spin
       if (cfg == 3) {

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "bh8_anim.cuh"
+#include "bh8_hud.h"
 
 struct bh8_script {
   bh8_ctx* ctx = nullptr;
@@ -281,6 +282,16 @@ int bh8_script_frame_constants(bh8_script* s, int frame, void* out, size_t bytes
 }
 
 void bh8_script_destroy(bh8_script* s) { script_free(s); }
+
+int bh8_draw_text(uint8_t* bgr, int rows, int cols, size_t row_stride_bytes, int x, int y, const char* text, int b,
+                  int g, int r) {
+  if (!bgr || !text || rows < 1 || cols < 1) return BH8_EINVAL;
+  if (row_stride_bytes == 0) row_stride_bytes = static_cast<size_t>(cols) * 3;
+  if (row_stride_bytes < static_cast<size_t>(cols) * 3) return BH8_EINVAL;
+  bh8_hud_draw(bgr, rows, cols, row_stride_bytes, x, y, text, static_cast<uint8_t>(b), static_cast<uint8_t>(g),
+               static_cast<uint8_t>(r));
+  return BH8_OK;
+}
 
 }  // extern "C"
 

@@ -75,6 +75,7 @@ def load_library(path=None):
                                            vp, C.c_size_t]),
         "bh8_frame_bytes": (C.c_size_t, []),
         "bh8_script_destroy": (None, [vp]),
+        "bh8_draw_text": (i32, [vp, i32, i32, C.c_size_t, i32, i32, C.c_char_p, i32, i32, i32]),
         "bh8_sink_open": (i32, [vp, C.c_char_p, i32, i32, C.c_double, i32, C.POINTER(vp)]),
         "bh8_sink_render": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params)]),
         "bh8_sink_submit": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params)]),
@@ -419,3 +420,16 @@ def merge_video_parts(part_paths, out_path):
     if rc != 0:
         raise Bh8Error(rc, (lib.bh8_last_error(None) or b"").decode())
     return frames.value, size.value
+
+
+def draw_text(frame_bgr, text, x, y, color=(0, 255, 0)):
+    """cv::putText(frame, text, {x, y}, FONT_HERSHEY_PLAIN, 1, color, 1) -- the reference's HUD text
+    (blackhole_solution_test.cc:313-325) -- on an (H, W, 3) uint8 BGR array, in place (bh8_draw_text)."""
+    lib = load_library()
+    assert frame_bgr.dtype == np.uint8 and frame_bgr.ndim == 3 and frame_bgr.shape[2] == 3
+    rc = lib.bh8_draw_text(frame_bgr.ctypes.data_as(C.c_void_p), frame_bgr.shape[0], frame_bgr.shape[1],
+                           frame_bgr.strides[0], int(x), int(y), text.encode("latin-1", "replace"),
+                           int(color[0]), int(color[1]), int(color[2]))
+    if rc != 0:
+        raise Bh8Error(rc, "bh8_draw_text: bad arguments")
+    return frame_bgr

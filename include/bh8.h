@@ -319,6 +319,13 @@ int bh8_host_frame_constants(const bh8_ctx* ctx, const bh8_scene* scene, const b
 size_t bh8_frame_bytes(void);
 void bh8_script_destroy(bh8_script* script);
 
+/* ---- HUD text (host) -------------------------------------------------------------------------------
+ * cv::putText(img, text, {x, y}, cv::FONT_HERSHEY_PLAIN, 1, {b, g, r}, 1) of blackhole_solution_test.cc:313-325
+ * on a CV_8UC3 (BGR) frame in HOST memory; (x, y) is the bottom-left corner of the text as in OpenCV.  For
+ * text inside the image the pixels equal OpenCV's bit for bit.  No GPU needed. */
+int bh8_draw_text(uint8_t* bgr, int rows, int cols, size_t row_stride_bytes, int x, int y, const char* text,
+                  int b, int g, int r);
+
 size_t bh8_pixel_bytes(int pixel_format);
 /* Bytes that travel host -> device per frame: the frame constants derived from the snapshot, passed as
  * kernel parameters (there is no other per-frame input). */

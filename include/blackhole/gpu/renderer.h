@@ -10,6 +10,7 @@
 #define BLACKHOLE_GPU_RENDERER_H_
 
 #include <cstring>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -112,6 +113,29 @@ class Renderer {
   friend class VideoWriter;
   friend class Script;
 };
+
+// The HUD of the reference's drivers (blackhole_solution_test.cc:309-326): five lines of green
+// FONT_HERSHEY_PLAIN text -- camera position, basis vectors, field of view -- drawn into the frame after
+// rendering.  bh8_draw_text reproduces cv::putText's pixels bit for bit, so this is a drop-in for that block
+// on frames that came back to the host.  Returns the lines it drew.
+template <typename T>
+std::vector<std::string> DrawHud(const Camera<T>& camera, cv::Mat* frame) {
+  std::vector<std::string> lines;
+  const auto add = [&](const char* label, const auto& value, const char* suffix = "") {
+    std::stringstream ss;
+    ss << value;
+    lines.push_back(std::string(label) + ss.str() + suffix);
+  };
+  add("Position: ", camera.focus());
+  add("VectorX: ", camera.vector_x());
+  add("VectorY: ", camera.vector_y());
+  add("VectorZ: ", camera.vector_z());
+  add("FoV: ", camera.fov() * 180.0 / blackhole::pi, " deg");
+  for (size_t k = 0; k < lines.size(); ++k)  // {0, 10}, {0, 25}, {0, 40}, {0, 55}, {0, 70}
+    bh8_draw_text(frame->data, frame->rows, frame->cols, static_cast<size_t>(frame->cols) * 3, 0,
+                  10 + 15 * static_cast<int>(k), lines[k].c_str(), 0, 255, 0);
+  return lines;
+}
 
 // A scripted animation: the Move* / Rotate* calls the reference's frame loop makes after
 // each frame (key handlers and the disc spin, blackhole_solution_test.cc:346-407), written down and
