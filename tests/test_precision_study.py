@@ -8,40 +8,20 @@ DESIGN.md 4.4: FP64 keeps hit class and key on 100 % of pixels; FP32 stepping al
 north_star's tolerance on detailed textures because a 1e-7 relative error in (u, phi) moves the hit
 point by a sizeable fraction of a texel and nearest-texel truncation turns that into colour flips.
 """
-import ctypes as C
-import os
-import subprocess
-
-import numpy as np
 import pytest
 
 import oracle_lib as O
 import parity
 import test_ray_math_host as H
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-_FP32 = None
-
-
-def fp32_harness():
-    global _FP32
-    if _FP32 is None:
-        out = os.path.join(HERE, "host_harness", "_build")
-        os.makedirs(out, exist_ok=True)
-        so = os.path.join(out, "libharness_fp32.so")
-        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-DBH8_FP32_STEPPING",
-                        "-I" + os.path.join(O.ROOT, "include"), "-I" + os.path.join(O.ROOT, "blackhole_8_b200", "csrc"),
-                        os.path.join(HERE, "host_harness", "harness.cc"), "-o", so], check=True)
-        _FP32 = C.CDLL(so)
-    return _FP32
+FP32 = ("BH8_FP32_STEPPING",)  # harness build variant: the geodesic update in float
 
 
 @pytest.mark.parametrize("name", ["cfg1_640x360", "cfg2_640x360", "cfg0_960x540"])
-def test_fp32_stepping_error_is_measured_and_fp64_is_clean(name, monkeypatch):
+def test_fp32_stepping_error_is_measured_and_fp64_is_clean(name):
     g = O.load_golden(name)
     fp64 = parity.compare(H.harness_render(g["snap"]), g)
-    monkeypatch.setattr(H, "_LIB", fp32_harness())
-    fp32 = parity.compare(H.harness_render(g["snap"]), g)
+    fp32 = parity.compare(H.harness_render(g["snap"], defines=FP32), g)
     print(name, "FP64:", {k: fp64[k] for k in ("class_agreement", "rgb_outlier_share", "exact_pixels")},
           "FP32 stepping:", {k: fp32[k] for k in ("class_agreement", "rgb_outlier_share", "exact_pixels",
                                                    "steps_agreement")})
