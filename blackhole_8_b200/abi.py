@@ -8,7 +8,7 @@ import json
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_OBJECTS = 16
 MAX_TEXTURES = 16
 
@@ -82,7 +82,21 @@ class Stats(C.Structure):
         ("tex_oob", C.c_uint64),
         ("kernel_ms", C.c_double),
         ("total_ms", C.c_double),
+        ("warps", C.c_uint64),
+        ("update_slots", C.c_uint64),
+        ("resolve_passes", C.c_uint64),
+        ("exact_tests", C.c_uint64),
     ]
+
+    def schedule(self):
+        """The warp schedule in the units DESIGN.md 4.2 uses (geodesic kernel, BH8_FLAG_STATS launches)."""
+        if not self.warps or not self.rays:
+            return None
+        return {"update_slots_per_warp": self.update_slots / self.warps,
+                "updates_per_ray": self.steps / self.rays,
+                "slot_utilisation": self.steps / (32.0 * self.update_slots) if self.update_slots else None,
+                "resolve_passes_per_warp": self.resolve_passes / self.warps,
+                "exact_tests_per_ray": self.exact_tests / self.rays}
 
 
 OP_MOVE_X, OP_MOVE_Y, OP_MOVE_Z, OP_ROTATE_X, OP_ROTATE_Y, OP_ROTATE_Z, OP_MOVE_TO = range(7)

@@ -54,9 +54,12 @@ struct Bh8Out {
   uint8_t* cls;
   int8_t* key;
   uint16_t* steps;
-  unsigned long long* stats;  // [0] rays [1] steps [2..5] class counts [6] tex_oob
-  int32_t vec_ok;             // 16-byte row stores are legal (width % 4 == 0, base 16-byte aligned)
+  unsigned long long* stats;  // [0] rays [1] steps [2..5] class counts [6] tex_oob [7] warps [8] update slots
+                              // [9] resolve passes [10] exact tests (see bh8_stats)
+  int32_t vec_ok;             // 16-byte row stores are legal: 4-byte formats width % 4 == 0, BGR8 width % 32 == 0;
+                              // base 16-byte aligned
 };
+constexpr int kStatSlots = 11;
 
 struct DeviceFetch {
   const Bh8Tex& tex;
@@ -71,10 +74,26 @@ struct DeviceFetch {
 __device__ __forceinline__ void store_pixel(const Bh8Frame& f, const Bh8Out& out, uint32_t* sh_rgba,
                                             unsigned long long* sh_red, int tid, int lane, int slot, int x0,
                                             int y0, int x, int y, bool inside, uint32_t bgr, uint32_t oob,
-                                            int cls, int key, int steps) {
+                                            int cls, int key, int steps, unsigned sched_slots = 0,
+                                            unsigned sched_passes = 0, unsigned sched_tests = 0) {
   const size_t gi = (size_t)y * f.width + x;
   if (f.pixel_format == BH8_PIXEL_BGR8) {
-    if (inside) {
+    if (out.vec_ok) {
+      // The reference's CV_8UC3 frame: a tile row is 32 x 3 = 96 contiguous bytes = six 16-byte stores
+      // (width % 32 == 0, so every tile is whole in x and 96 x0/32 keeps the alignment).
+      uint8_t* sb = reinterpret_cast<uint8_t*>(sh_rgba) + slot * 3;
+      sb[0] = (uint8_t)bgr;
+      sb[1] = (uint8_t)(bgr >> 8);
+      sb[2] = (uint8_t)(bgr >> 16);
+      __syncthreads();
+      if (tid < kTileH * 6) {
+        const int row = tid / 6, q = tid - row * 6;
+        if (y0 + row < f.height) {
+          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(sh_rgba) + row * 96 + q * 16);
+          *reinterpret_cast<uint4*>(out.pixels + ((size_t)(y0 + row) * f.width + x0) * 3 + q * 16) = v;
+        }
+      }
+    } else if (inside) {
       uint8_t* d = out.pixels + gi * 3;
       d[0] = (uint8_t)bgr;
       d[1] = (uint8_t)(bgr >> 8);
@@ -106,32 +125,38 @@ __device__ __forceinline__ void store_pixel(const Bh8Frame& f, const Bh8Out& out
 
   // ---- optional counters ----------------------------------------------------------------------------
   if (f.flags & BH8_FLAG_STATS) {
-    if (tid < 7) sh_red[tid] = 0ull;
+    if (tid < kStatSlots) sh_red[tid] = 0ull;
     __syncthreads();
-    unsigned long long v[7];
+    unsigned long long v[kStatSlots];
     v[0] = inside ? 1ull : 0ull;
     v[1] = inside ? (unsigned long long)steps : 0ull;
     for (int k = 0; k < 4; ++k) v[2 + k] = (inside && cls == k) ? 1ull : 0ull;
     v[6] = oob;
+    // the warp schedule (bh8_render_kernel's STATS instantiation; 0 elsewhere): per warp, so lane 0 speaks
+    v[7] = (lane == 0) ? 1ull : 0ull;
+    v[8] = (lane == 0) ? sched_slots : 0ull;
+    v[9] = (lane == 0) ? sched_passes : 0ull;
+    v[10] = sched_tests;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
+    for (int k = 0; k < kStatSlots; ++k) {
       unsigned long long s = v[k];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0 && s) atomicAdd(&sh_red[k], s);
     }
     __syncthreads();
-    if (tid < 7 && sh_red[tid]) atomicAdd(&out.stats[tid], sh_red[tid]);
+    if (tid < kStatSlots && sh_red[tid]) atomicAdd(&out.stats[tid], sh_red[tid]);
   }
 }
 
-// One 32x8 tile of the frame.  `f` is in the constant bank either way -- a __grid_constant__ kernel
-// parameter (bh8_render_kernel) or the __constant__ frame a script renders from
-// (bh8_render_kernel_script) -- so its fields are direct operands of the FP64 instructions.
-template <int NN>
+// One 32x8 tile of the frame.  `f` is a __grid_constant__ kernel parameter, i.e. in the constant bank:
+// its fields are direct operands of the FP64 instructions.
+// STATS: the instantiation BH8_FLAG_STATS launches take -- it also counts the warp schedule (update slots,
+// resolve passes, exact tests); the plain one carries no counter through the stepping loop.
+template <int NN, bool STATS>
 __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex, const Bh8Out& out) {
   __shared__ __align__(16) uint32_t sh_rgba[kThreads];
-  __shared__ unsigned long long sh_red[7];
+  __shared__ unsigned long long sh_red[kStatSlots];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
 
@@ -175,16 +200,22 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
     lane_park_constants(L, mail);
   }
   int waited = 0;
+  unsigned n_iter = 0, n_pass = 0, n_test = 0;
   for (;;) {
     // Lean stepping: the same straight-line update for every lane (frozen lanes are inert, see
     // lane_freeze), a few updates per round of warp votes.
 #pragma unroll
     for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k) lane_update(f, L, mail);
+    if (STATS) ++n_iter;
     const unsigned present = __reduce_or_sync(0xffffffffu, (unsigned)L.state);
     const int todo = warp_decide(present, waited, f.resolve_wait);
     if (todo == kWarpStep) continue;
     if (todo == kWarpDone) break;  // every ray of the patch has ended
-    if (L.state & (kPend | kPendChord)) lane_resolve(f, L, mail);
+    if (STATS) ++n_pass;
+    if (L.state & (kPend | kPendChord)) {
+      if (STATS) ++n_test;
+      lane_resolve(f, L, mail);
+    }
   }
   const int steps = inside ? mail.get_w(kMwSteps) : 0;
   const int hit_obj = inside ? mail.get_w(kMwHit) : -1;
@@ -197,31 +228,21 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
     cls = f.obj[hit_obj].cls;
     key = f.obj[hit_obj].key;
   }
-  store_pixel(f, out, sh_rgba, sh_red, tid, lane, slot, x0, y0, x, y, inside, bgr, oob, cls, key, steps);
+  store_pixel(f, out, sh_rgba, sh_red, tid, lane, slot, x0, y0, x, y, inside, bgr, oob, cls, key, steps,
+              n_iter * BH8_UPDATES_PER_VOTE, n_pass, n_test);
 }
 
-template <int NN>
+template <int NN, bool STATS>
 __global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
 bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
-  render_tile<NN>(f, tex, out);
-}
-
-// Scripted animation: the frame constants were built ON THE DEVICE
-// (bh8_build_frames_kernel) and are copied device-to-device into this symbol in stream order right
-// before the launch; no per-frame data comes from the host.
-__constant__ Bh8Frame c_script_frame;
-
-template <int NN>
-__global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
-bh8_render_kernel_script(const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
-  render_tile<NN>(c_script_frame, tex, out);
+  render_tile<NN, STATS>(f, tex, out);
 }
 
 // Flat-space tracer (BH8_TRACER_LINEAR): one thread per pixel, at most linear_steps segment tests,
 // same tile mapping, colour and store path as the geodesic kernel.
 __device__ __forceinline__ void linear_tile(const Bh8Frame& f, const Bh8Tex& tex, const Bh8Out& out) {
   __shared__ __align__(16) uint32_t sh_rgba[kThreads];
-  __shared__ unsigned long long sh_red[7];
+  __shared__ unsigned long long sh_red[kStatSlots];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int x0 = blockIdx.x * kTileW;
@@ -257,11 +278,6 @@ __device__ __forceinline__ void linear_tile(const Bh8Frame& f, const Bh8Tex& tex
 __global__ void __launch_bounds__(kThreads, 4)
 bh8_linear_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
   linear_tile(f, tex, out);
-}
-
-__global__ void __launch_bounds__(kThreads, 4)
-bh8_linear_kernel_script(const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
-  linear_tile(c_script_frame, tex, out);
 }
 
 // Precision study: the bare geodesic update chain (u += du; G; rsqrt; trapezoid; two compares) for

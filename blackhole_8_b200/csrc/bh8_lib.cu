@@ -30,7 +30,7 @@ struct Device {
   cudaStream_t slot_stream[2] = {nullptr, nullptr};
   cudaArray_t tex_array[BH8_MAX_TEXTURES] = {};
   cudaTextureObject_t tex_obj[BH8_MAX_TEXTURES] = {};
-  unsigned long long* d_stats = nullptr;  // 8 counters
+  unsigned long long* d_stats = nullptr;  // 16 counters (bh8::kStatSlots used)
   // double-buffered frame staging for bh8_render()
   void* d_pix[2] = {nullptr, nullptr};
   uint8_t* d_cls[2] = {nullptr, nullptr};
@@ -97,13 +97,10 @@ int make_grid(const Bh8Frame& f, dim3* grid) {
   return BH8_OK;
 }
 
-int launch_frame(bh8_ctx* ctx, Device& d, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
-                 void* d_pixels, void* d_cls, void* d_key, void* d_steps, cudaStream_t st = nullptr) {
-  if (!st) st = d.stream;
-  Bh8Frame f;
-  char msg[192];
-  const int rc = bh8_build_frame(scene, cam, prm, ctx->tex_rows, ctx->tex_cols, &f, msg);
-  if (rc != BH8_OK) return fail(ctx, rc, msg);
+// Launch the render kernel for frame constants that are already built (by bh8_build_frame here, or
+// on the device by a script and read back once at its creation).
+int launch_built(bh8_ctx* ctx, Device& d, Bh8Frame& f, void* d_pixels, void* d_cls, void* d_key, void* d_steps,
+                 cudaStream_t st) {
   dim3 grid;
   if (make_grid(f, &grid) != BH8_OK)
     return fail(ctx, BH8_EINVAL, "stripe_rows must be a multiple of 8 when shard_count > 1");
@@ -117,30 +114,50 @@ int launch_frame(bh8_ctx* ctx, Device& d, const bh8_scene* scene, const bh8_came
   out.key = static_cast<int8_t*>(d_key);
   out.steps = static_cast<uint16_t*>(d_steps);
   out.stats = d.d_stats;
-  out.vec_ok = (f.width % 4 == 0) && (reinterpret_cast<uintptr_t>(d_pixels) % 16 == 0) &&
-               f.pixel_format != BH8_PIXEL_BGR8;
+  const bool aligned = reinterpret_cast<uintptr_t>(d_pixels) % 16 == 0;
+  out.vec_ok = aligned && (f.pixel_format == BH8_PIXEL_BGR8 ? f.width % 32 == 0 : f.width % 4 == 0);
   BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
-  if (ctx->resolve_wait != 0x7fffffff) f.resolve_wait = ctx->resolve_wait;  // tuning knob
-  if (prm->flags & BH8_FLAG_NO_BATCHING) f.resolve_wait = -1;  // exact tests run at once
-  // One instantiation per number of non-central planes with an FP32 side filter; scenes with more
-  // planes than filter slots take the generic instantiation (exact test on every gated step).
   if (f.tracer == BH8_TRACER_LINEAR) {
     bh8::bh8_linear_kernel<<<grid, bh8::kThreads, 0, st>>>(f, tex, out);
     BH8_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return BH8_OK;
   }
-  switch (f.n_nc <= bh8::kMaxFilterPlanes ? f.n_nc : -1) {
-    case 0: bh8::bh8_render_kernel<0><<<grid, bh8::kThreads, 0, st>>>(f, tex, out); break;
-    case 1: bh8::bh8_render_kernel<1><<<grid, bh8::kThreads, 0, st>>>(f, tex, out); break;
-    case 2: bh8::bh8_render_kernel<2><<<grid, bh8::kThreads, 0, st>>>(f, tex, out); break;
-    case 3: bh8::bh8_render_kernel<3><<<grid, bh8::kThreads, 0, st>>>(f, tex, out); break;
-    case 4: bh8::bh8_render_kernel<4><<<grid, bh8::kThreads, 0, st>>>(f, tex, out); break;
-    default: bh8::bh8_render_kernel<-1><<<grid, bh8::kThreads, 0, st>>>(f, tex, out); break;
+  // One instantiation per number of non-central planes with an FP32 side filter; scenes with more
+  // planes than filter slots take the generic instantiation (exact test on every gated step).
+  // BH8_FLAG_STATS launches take the instantiation that also counts the warp schedule.
+  const int nn = f.n_nc <= bh8::kMaxFilterPlanes ? f.n_nc : -1;
+#define BH8_LAUNCH(NN_)                                                                    \
+  do {                                                                                     \
+    if (f.flags & BH8_FLAG_STATS)                                                          \
+      bh8::bh8_render_kernel<NN_, true><<<grid, bh8::kThreads, 0, st>>>(f, tex, out);      \
+    else                                                                                   \
+      bh8::bh8_render_kernel<NN_, false><<<grid, bh8::kThreads, 0, st>>>(f, tex, out);     \
+  } while (0)
+  switch (nn) {
+    case 0: BH8_LAUNCH(0); break;
+    case 1: BH8_LAUNCH(1); break;
+    case 2: BH8_LAUNCH(2); break;
+    case 3: BH8_LAUNCH(3); break;
+    case 4: BH8_LAUNCH(4); break;
+    default: BH8_LAUNCH(-1); break;
   }
+#undef BH8_LAUNCH
   BH8_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   return BH8_OK;
+}
+
+int launch_frame(bh8_ctx* ctx, Device& d, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
+                 void* d_pixels, void* d_cls, void* d_key, void* d_steps, cudaStream_t st = nullptr) {
+  if (!st) st = d.stream;
+  Bh8Frame f;
+  char msg[192];
+  const int rc = bh8_build_frame(scene, cam, prm, ctx->tex_rows, ctx->tex_cols, &f, msg);
+  if (rc != BH8_OK) return fail(ctx, rc, msg);
+  if (ctx->resolve_wait != 0x7fffffff) f.resolve_wait = ctx->resolve_wait;  // tuning knob
+  if (prm->flags & BH8_FLAG_NO_BATCHING) f.resolve_wait = -1;  // exact tests run at once
+  return launch_built(ctx, d, f, d_pixels, d_cls, d_key, d_steps, st);
 }
 
 int ensure_staging(bh8_ctx* ctx, Device& d, size_t pixels) {
@@ -171,8 +188,11 @@ int ensure_staging(bh8_ctx* ctx, Device& d, size_t pixels) {
 int read_stats(bh8_ctx* ctx, bh8_stats* s) {
   for (int i = 0; i < ctx->n_dev; ++i) {
     Device& d = ctx->dev[i];
-    unsigned long long h[8];
+    unsigned long long h[16];
     BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+    // launches that add to the counters may sit on any of the device's streams
+    BH8_CUDA(ctx, cudaStreamSynchronize(d.copy_stream));
+    for (int b = 0; b < 2; ++b) BH8_CUDA(ctx, cudaStreamSynchronize(d.slot_stream[b]));
     BH8_CUDA(ctx, cudaMemcpyAsync(h, d.d_stats, sizeof h, cudaMemcpyDeviceToHost, d.stream));
     BH8_CUDA(ctx, cudaMemsetAsync(d.d_stats, 0, sizeof h, d.stream));
     BH8_CUDA(ctx, cudaStreamSynchronize(d.stream));
@@ -180,6 +200,10 @@ int read_stats(bh8_ctx* ctx, bh8_stats* s) {
     s->steps += h[1];
     for (int c = 0; c < 4; ++c) s->class_count[c] += h[2 + c];
     s->tex_oob += h[6];
+    s->warps += h[7];
+    s->update_slots += h[8];
+    s->resolve_passes += h[9];
+    s->exact_tests += h[10];
   }
   return BH8_OK;
 }
@@ -240,8 +264,8 @@ int bh8_create(bh8_ctx** out, const int* devices, int n_dev) {
     BH8_CREATE_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     BH8_CREATE_CUDA(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; ++b) BH8_CREATE_CUDA(cudaStreamCreateWithFlags(&d.slot_stream[b], cudaStreamNonBlocking));
-    BH8_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.d_stats), 8 * sizeof(unsigned long long)));
-    BH8_CREATE_CUDA(cudaMemset(d.d_stats, 0, 8 * sizeof(unsigned long long)));
+    BH8_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.d_stats), 16 * sizeof(unsigned long long)));
+    BH8_CREATE_CUDA(cudaMemset(d.d_stats, 0, 16 * sizeof(unsigned long long)));
     for (int b = 0; b < 2; ++b) {
       BH8_CREATE_CUDA(cudaEventCreateWithFlags(&d.ev_kernel_done[b], cudaEventDisableTiming));
       BH8_CREATE_CUDA(cudaEventCreateWithFlags(&d.ev_copy_done[b], cudaEventDisableTiming));
@@ -390,9 +414,48 @@ int bh8_read_stats(bh8_ctx* ctx, bh8_stats* stats) {
   return read_stats(ctx, stats);
 }
 
+namespace {
+// After a failure in the middle of a batch: nothing may still be writing into the caller's buffers
+// when the call returns.
+void drain_all(bh8_ctx* ctx) {
+  for (int i = 0; i < ctx->n_dev; ++i) {
+    Device& d = ctx->dev[i];
+    if (cudaSetDevice(d.ordinal) != cudaSuccess) continue;
+    cudaStreamSynchronize(d.stream);
+    cudaStreamSynchronize(d.copy_stream);
+    for (int b = 0; b < 2; ++b) cudaStreamSynchronize(d.slot_stream[b]);
+  }
+  (void)cudaGetLastError();
+}
+int render_batch(bh8_ctx* ctx, const bh8_scene* scenes, const bh8_camera* cams, int n_frames, const bh8_params* params,
+                 uint8_t* out_pixels, uint8_t* out_class, int8_t* out_key, uint16_t* out_steps, bh8_stats* stats);
+}  // namespace
+
 int bh8_render(bh8_ctx* ctx, const bh8_scene* scenes, const bh8_camera* cams, int n_frames, const bh8_params* params,
                uint8_t* out_pixels, uint8_t* out_class, int8_t* out_key, uint16_t* out_steps, bh8_stats* stats) {
   if (!ctx) return BH8_EINVAL;
+  // bh8_render shares the staging buffers with bh8_submit: frames still in flight there finish first
+  for (int i = 0; i < ctx->n_dev; ++i)
+    for (int b = 0; b < 2; ++b)
+      if (ctx->dev[i].slot_busy[b]) {
+        BH8_CUDA(ctx, cudaSetDevice(ctx->dev[i].ordinal));
+        BH8_CUDA(ctx, cudaEventSynchronize(ctx->dev[i].ev_copy_done[b]));
+        ctx->dev[i].slot_busy[b] = false;
+      }
+  const int rc = render_batch(ctx, scenes, cams, n_frames, params, out_pixels, out_class, out_key, out_steps, stats);
+  if (rc != BH8_OK) {
+    const std::string keep = ctx->err;
+    drain_all(ctx);
+    ctx->err = keep;
+  }
+  return rc;
+}
+
+} // extern "C"
+
+namespace {
+int render_batch(bh8_ctx* ctx, const bh8_scene* scenes, const bh8_camera* cams, int n_frames, const bh8_params* params,
+                 uint8_t* out_pixels, uint8_t* out_class, int8_t* out_key, uint16_t* out_steps, bh8_stats* stats) {
   if (!scenes || !cams || !params || !out_pixels || n_frames < 1) return fail(ctx, BH8_EINVAL, "bad arguments to bh8_render");
   const auto wall0 = std::chrono::steady_clock::now();
   const size_t bpp = bh8_pixel_bytes(params->pixel_format);
@@ -507,6 +570,9 @@ int bh8_render(bh8_ctx* ctx, const bh8_scene* scenes, const bh8_camera* cams, in
   }
   return BH8_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int bh8_submit(bh8_ctx* ctx, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* params,
                uint8_t* out_pixels, uint64_t* ticket) {
@@ -625,7 +691,37 @@ int bh8_memset_d(bh8_ctx* ctx, void* d_ptr, int value, size_t bytes) {
 }
 
 int bh8_host_alloc(void** p, size_t bytes) {
-  return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? BH8_OK : BH8_ENOMEM;
+  // portable: pinned for every CUDA context of the process (multi-device contexts read back into one buffer)
+  return cudaHostAlloc(p, bytes, cudaHostAllocPortable) == cudaSuccess ? BH8_OK : BH8_ENOMEM;
+}
+
+int bh8_host_alloc_flags(void** p, size_t bytes, unsigned flags) {
+  unsigned f = cudaHostAllocPortable;
+  if (flags & BH8_HOST_WRITE_COMBINED) f |= cudaHostAllocWriteCombined;
+  return cudaHostAlloc(p, bytes, f) == cudaSuccess ? BH8_OK : BH8_ENOMEM;
+}
+
+int bh8_measure_d2h(bh8_ctx* ctx, uint8_t* host_a, uint8_t* host_b, size_t bytes, int reps, double* seconds) {
+  if (!ctx || !host_a || !host_b || bytes == 0 || reps < 1 || !seconds) return BH8_EINVAL;
+  Device& d = ctx->dev[0];
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  {
+    const int rc = ensure_staging(ctx, d, (bytes + 3) / 4);
+    if (rc != BH8_OK) return rc;
+  }
+  for (int b = 0; b < 2; ++b) BH8_CUDA(ctx, cudaStreamSynchronize(d.slot_stream[b]));
+  // the copies bh8_submit queues, without the kernels: staging slot b -> host buffer b on slot stream b,
+  // at most one copy per slot in flight
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < reps; ++i) {
+    const int b = i & 1;
+    if (i >= 2) BH8_CUDA(ctx, cudaEventSynchronize(d.ev_copy_done[b]));
+    BH8_CUDA(ctx, cudaMemcpyAsync(b ? host_b : host_a, d.d_pix[b], bytes, cudaMemcpyDeviceToHost, d.slot_stream[b]));
+    BH8_CUDA(ctx, cudaEventRecord(d.ev_copy_done[b], d.slot_stream[b]));
+  }
+  for (int b = 0; b < 2; ++b) BH8_CUDA(ctx, cudaStreamSynchronize(d.slot_stream[b]));
+  *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return BH8_OK;
 }
 
 int bh8_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? BH8_OK : BH8_ECUDA; }

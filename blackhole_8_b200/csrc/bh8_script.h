@@ -17,7 +17,12 @@ struct bh8_script {
   Bh8Frame* d_frames = nullptr;
   bh8_camera* d_cams = nullptr;
   bh8_object* d_objs = nullptr;
-  std::vector<int> n_nc;  // per frame: which instantiation of the render kernel it takes
+  // The frame constants the device built, read back ONCE at creation: a launch passes frame k's as the
+  // kernel's __grid_constant__ parameter, exactly as a host-built frame travels.  (They used to be copied
+  // device-to-device into one module-wide __constant__ symbol before each launch; two contexts
+  // rendering scripts on the same GPU could then overwrite each other's constants under a running
+  // kernel.  A parameter belongs to its launch.)
+  std::vector<Bh8Frame> h_frames;
   // bh8_script_render_range: the captured launch sequence of the last range drawn
   cudaGraphExec_t graph = nullptr;
   int g_first = -1, g_count = 0;
@@ -26,11 +31,6 @@ struct bh8_script {
 };
 
 namespace {
-
-template <int NN>
-void launch_script_kernel(dim3 grid, cudaStream_t st, const bh8::Bh8Tex& tex, const bh8::Bh8Out& out) {
-  bh8::bh8_render_kernel_script<NN><<<grid, bh8::kThreads, 0, st>>>(tex, out);
-}
 
 void script_free(bh8_script* s) {
   if (!s) return;
@@ -68,7 +68,7 @@ int bh8_script_create(bh8_ctx* ctx, const bh8_scene* scene0, const bh8_basis* ob
   if (!ctx) return BH8_EINVAL;
   if (!out) return fail(ctx, BH8_EINVAL, "bh8_script_create: null out");
   *out = nullptr;
-  if (!scene0 || !scene0->obj || !cam0 || !params || n_frames < 1 || n_frames > (1 << 24) || n_actions < 0 ||
+  if (!scene0 || !scene0->obj || !cam0 || !params || n_frames < 1 || n_frames > (1 << 16) || n_actions < 0 ||
       (n_actions > 0 && !actions))
     return fail(ctx, BH8_EINVAL, "bad arguments to bh8_script_create");
   if (scene0->n_obj < 1 || scene0->n_obj > BH8_MAX_OBJECTS) return fail(ctx, BH8_EINVAL, "n_obj out of range");
@@ -100,6 +100,7 @@ int bh8_script_create(bh8_ctx* ctx, const bh8_scene* scene0, const bh8_basis* ob
   bh8_object* d_proto = nullptr;
   int* d_status = nullptr;
   std::vector<int> status(2 * static_cast<size_t>(n_frames));
+  s->h_frames.resize(static_cast<size_t>(n_frames));
   cudaError_t e = cudaSuccess;
   const auto step = [&](cudaError_t r) {
     if (e == cudaSuccess) e = r;
@@ -132,6 +133,8 @@ int bh8_script_create(bh8_ctx* ctx, const bh8_scene* scene0, const bh8_basis* ob
       ctx->launches += 2;
     }
     step(cudaMemcpyAsync(status.data(), d_status, status.size() * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+    step(cudaMemcpyAsync(s->h_frames.data(), s->d_frames, s->h_frames.size() * sizeof(Bh8Frame),
+                         cudaMemcpyDeviceToHost, d.stream));
     step(cudaStreamSynchronize(d.stream));
   }
   cudaFree(d_ent);
@@ -142,7 +145,6 @@ int bh8_script_create(bh8_ctx* ctx, const bh8_scene* scene0, const bh8_basis* ob
     script_free(s);
     return fail(ctx, BH8_ECUDA, std::string("bh8_script_create: ") + cudaGetErrorString(e));
   }
-  s->n_nc.resize(n_frames);
   for (int k = 0; k < n_frames; ++k) {
     if (status[2 * k] != BH8F_OK) {
       const int reason = status[2 * k];
@@ -150,7 +152,6 @@ int bh8_script_create(bh8_ctx* ctx, const bh8_scene* scene0, const bh8_basis* ob
       return fail(ctx, bh8_frame_error_code(reason),
                   "bh8_script_create: frame " + std::to_string(k) + ": " + bh8_frame_error_text(reason));
     }
-    s->n_nc[k] = status[2 * k + 1];
   }
   *out = s;
   return BH8_OK;
@@ -164,46 +165,8 @@ int bh8_script_render(bh8_script* s, int frame, void* d_pixels, void* d_class, v
   if (frame < 0 || frame >= s->n_frames) return fail(ctx, BH8_EINVAL, "bh8_script_render: frame out of range");
   if (!d_pixels) return fail(ctx, BH8_EINVAL, "null pixel buffer");
   Device& d = ctx->dev[0];
-  Bh8Frame shape;  // make_grid reads the frame size and the stripe sharding only
-  shape.width = s->width;
-  shape.height = s->height;
-  shape.stripe_rows = s->prm.stripe_rows;
-  shape.shard_index = s->prm.shard_index;
-  shape.shard_count = s->prm.shard_count;
-  dim3 grid;
-  if (make_grid(shape, &grid) != BH8_OK)
-    return fail(ctx, BH8_EINVAL, "stripe_rows must be a multiple of 8 when shard_count > 1");
-  if (grid.y == 0) return BH8_OK;
-  bh8::Bh8Tex tex;
-  for (int i = 0; i < BH8_MAX_TEXTURES; ++i) tex.obj[i] = d.tex_obj[i];
-  bh8::Bh8Out out;
-  out.pixels = static_cast<uint8_t*>(d_pixels);
-  out.cls = static_cast<uint8_t*>(d_class);
-  out.key = static_cast<int8_t*>(d_key);
-  out.steps = static_cast<uint16_t*>(d_steps);
-  out.stats = d.d_stats;
-  out.vec_ok = (s->width % 4 == 0) && (reinterpret_cast<uintptr_t>(d_pixels) % 16 == 0) &&
-               s->prm.pixel_format != BH8_PIXEL_BGR8;
-  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
-  // Frame constants: device -> constant bank, in stream order (after the previous frame's kernel).
-  BH8_CUDA(ctx, cudaMemcpyToSymbolAsync(bh8::c_script_frame, s->d_frames + frame, sizeof(Bh8Frame), 0,
-                                        cudaMemcpyDeviceToDevice, d.stream));
-  if (s->prm.tracer == BH8_TRACER_LINEAR) {
-    bh8::bh8_linear_kernel_script<<<grid, bh8::kThreads, 0, d.stream>>>(tex, out);
-  } else {
-    const int nn = s->n_nc[frame];
-    switch (nn <= bh8::kMaxFilterPlanes ? nn : -1) {
-      case 0: launch_script_kernel<0>(grid, d.stream, tex, out); break;
-      case 1: launch_script_kernel<1>(grid, d.stream, tex, out); break;
-      case 2: launch_script_kernel<2>(grid, d.stream, tex, out); break;
-      case 3: launch_script_kernel<3>(grid, d.stream, tex, out); break;
-      case 4: launch_script_kernel<4>(grid, d.stream, tex, out); break;
-      default: launch_script_kernel<-1>(grid, d.stream, tex, out); break;
-    }
-  }
-  BH8_CUDA(ctx, cudaGetLastError());
-  ctx->launches++;
-  return BH8_OK;
+  Bh8Frame f = s->h_frames[frame];
+  return launch_built(ctx, d, f, d_pixels, d_class, d_key, d_steps, d.stream);
 }
 
 int bh8_script_render_range(bh8_script* s, int first, int count, void* d_base, size_t frame_stride_bytes) {
@@ -222,8 +185,8 @@ int bh8_script_render_range(bh8_script* s, int first, int count, void* d_base, s
       cudaGraphExecDestroy(s->graph);
       s->graph = nullptr;
     }
-    // Capture what `count` bh8_script_render() calls enqueue -- constants to the symbol, kernel, next
-    // frame -- into one graph: the whole range then costs the host a single launch.
+    // Capture what `count` bh8_script_render() calls enqueue -- one kernel per frame, its constants in
+    // the node's parameters -- into one graph: the whole range then costs the host a single launch.
     const uint64_t launches_before = ctx->launches;
     BH8_CUDA(ctx, cudaStreamBeginCapture(d.stream, cudaStreamCaptureModeThreadLocal));
     int rc = BH8_OK;

@@ -61,6 +61,8 @@ def load_library(path=None):
         "bh8_memcpy_d2h": (i32, [vp, vp, vp, C.c_size_t]),
         "bh8_memset_d": (i32, [vp, vp, i32, C.c_size_t]),
         "bh8_host_alloc": (i32, [C.POINTER(vp), C.c_size_t]),
+        "bh8_host_alloc_flags": (i32, [C.POINTER(vp), C.c_size_t, C.c_uint]),
+        "bh8_measure_d2h": (i32, [vp, vp, vp, C.c_size_t, i32, C.POINTER(C.c_double)]),
         "bh8_host_free": (i32, [vp]),
         "bh8_measure_fp64_peak": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "bh8_measure_stepping": (i32, [vp, i32, C.POINTER(C.c_double)]),
@@ -102,11 +104,11 @@ def load_library(path=None):
 class PinnedBuffer:
     """cudaHostAlloc'ed host memory viewed as a numpy array."""
 
-    def __init__(self, lib, shape, dtype):
+    def __init__(self, lib, shape, dtype, write_combined=False):
         self._lib = lib
         self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         p = C.c_void_p()
-        rc = lib.bh8_host_alloc(C.byref(p), max(1, self.nbytes))
+        rc = lib.bh8_host_alloc_flags(C.byref(p), max(1, self.nbytes), 1 if write_combined else 0)
         if rc != 0:
             raise Bh8Error(rc, "cudaHostAlloc failed")
         self.ptr = p.value
@@ -266,8 +268,15 @@ class Renderer:
     def ipc_close(self, d_ptr):
         self._check(self.lib.bh8_ipc_close(self._ctx, C.c_void_p(d_ptr)))
 
-    def pinned(self, shape, dtype=np.uint8):
-        return PinnedBuffer(self.lib, shape, dtype)
+    def pinned(self, shape, dtype=np.uint8, write_combined=False):
+        return PinnedBuffer(self.lib, shape, dtype, write_combined)
+
+    def measure_d2h(self, buf_a, buf_b, nbytes, reps):
+        """Seconds for `reps` read-backs of nbytes each into the two pinned buffers, no kernels (bh8_measure_d2h)."""
+        s = C.c_double()
+        self._check(self.lib.bh8_measure_d2h(self._ctx, C.c_void_p(buf_a.ptr), C.c_void_p(buf_b.ptr), nbytes, reps,
+                                             C.byref(s)))
+        return s.value
 
     def host_frame_constants(self, snap, nstep=None, pixel_format=abi.PIXEL_RGBA8, flags=0):
         """The frame constants the host derives from a snapshot (what every non-scripted launch passes)."""

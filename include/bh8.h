@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BH8_ABI_VERSION 4
+#define BH8_ABI_VERSION 5
 #define BH8_MAX_OBJECTS 16
 #define BH8_MAX_TEXTURES 16
 #define BH8_MAX_DEVICES 8
@@ -140,6 +140,16 @@ typedef struct bh8_stats {
   uint64_t tex_oob;      /* texture fetches whose reference index lay outside the image (clamped) */
   double kernel_ms;      /* device time of the render kernel(s), CUDA events, max over devices */
   double total_ms;       /* host wall time of the call */
+  /* The warp schedule of the geodesic kernel (0 for the linear tracer).  A warp (an 8x4-pixel patch) runs
+   * the same geodesic update for its 32 lanes until its last ray has ended:
+   *   update_slots / warps      updates a warp issued; its rays needed steps / rays each on average, so
+   *                             steps / (32 * update_slots) of the issued lane-updates moved a ray
+   *   resolve_passes / warps    times a warp ran its parked exact segment tests (FindCollision) together
+   *   exact_tests / rays        exact tests per ray */
+  uint64_t warps;
+  uint64_t update_slots;
+  uint64_t resolve_passes;
+  uint64_t exact_tests;
 } bh8_stats;
 
 typedef struct bh8_ctx bh8_ctx;
@@ -205,7 +215,13 @@ int bh8_ipc_close(bh8_ctx* ctx, void* d_ptr);
 int bh8_memcpy_d2h(bh8_ctx* ctx, void* host, const void* d_ptr, size_t bytes);
 /* Pinned host memory (cudaHostAlloc) so the frame read-back of bh8_render() is a true async DMA. */
 int bh8_host_alloc(void** p, size_t bytes);
+#define BH8_HOST_WRITE_COMBINED 1u /* cudaHostAllocWriteCombined: faster DMA target, slow for the CPU to read */
+int bh8_host_alloc_flags(void** p, size_t bytes, unsigned flags);
 int bh8_host_free(void* p);
+/* Read-back ceiling of this process' GPU: `reps` device-to-host copies of `bytes` each, alternating
+ * between the two pinned buffers exactly as bh8_submit() queues its frames' read-backs (staging slot ->
+ * host, one copy per slot in flight) but with no kernel in between; wall time in *seconds. */
+int bh8_measure_d2h(bh8_ctx* ctx, uint8_t* host_a, uint8_t* host_b, size_t bytes, int reps, double* seconds);
 int bh8_memset_d(bh8_ctx* ctx, void* d_ptr, int value, size_t bytes);
 
 /* FP64 pipe peak: runs a dependent-free DFMA chain on every SM of device 0 and reports the

@@ -37,7 +37,7 @@ def test_abi_version_and_struct_sizes(lib):
     assert C.sizeof(abi.Object) == 16 + (15 + 9 + 4) * 8
     assert C.sizeof(abi.Scene) == 16
     assert C.sizeof(abi.Params) == 32
-    assert C.sizeof(abi.Stats) == 9 * 8
+    assert C.sizeof(abi.Stats) == 13 * 8
     assert lib.bh8_pixel_bytes(abi.PIXEL_BGR8) == 3 and lib.bh8_pixel_bytes(abi.PIXEL_RGBA8) == 4
 
 
