@@ -54,6 +54,9 @@ struct Bh8Frame {
   // integration
   int32_t nstep, n_obj, bh_index, n_central;
   int32_t tracer, linear_steps;  // BH8_TRACER_*; segments per ray of the linear tracer
+  // step indices at which a ray's leg changes (lane_event): the 0.9-step (nstep - 1), the first outbound
+  // step / captured chord (nstep) and the end of the ray (2 nstep - 1)
+  int32_t evt_turn, evt_back, evt_end, evt_pad;
   double inv_nstep;
   // conservative filters (see bh8_ray.cuh)
   double u_gate;        // non-central planes can only be crossed while min(u) <= u_gate
@@ -213,6 +216,9 @@ BH8F_HD int bh8_build_frame_core(const bh8_scene* scene, const bh8_camera* cam, 
   f->linear_steps = prm->linear_steps;
   f->nstep = linear ? 2 : prm->nstep;
   f->inv_nstep = BH8F_DIV(1.0, (double)f->nstep);
+  f->evt_turn = f->nstep - 1;
+  f->evt_back = f->nstep;
+  f->evt_end = 2 * f->nstep - 1;
   f->n_obj = scene->n_obj;
   f->bh_index = scene->bh_index;
   f->pixel_format = prm->pixel_format;

@@ -199,30 +199,57 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
     lane_setup(f, x, y, L, mail);
     lane_park_constants(L, mail);
   }
-  int waited = 0;
+  const DeviceFetch fetch{tex};
+  // The two FP64 constants of the geodesic update (2M, 3/8) go through shared memory once per warp so
+  // that the stepping loop holds them in registers: see StepConst.
+  __shared__ double sh_step_const[kThreads / 32][2];
+  if (lane == 0) {
+    sh_step_const[warp][0] = f.two_m;
+    sh_step_const[warp][1] = 0.375;
+  }
+  __syncwarp();
+  const uint32_t sc_addr = (uint32_t)__cvta_generic_to_shared(&sh_step_const[warp][0]);
   unsigned n_iter = 0, n_pass = 0, n_test = 0;
-  for (;;) {
+  for (bool done = false; !done;) {
     // Lean stepping: the same straight-line update for every lane (frozen lanes are inert, see
-    // lane_freeze), a few updates per round of warp votes.
+    // lane_freeze), a few updates per round of warp votes, until the warp decides to attend to its
+    // parked lanes (or every ray has ended).  `waited` and the update's constants live in this phase
+    // only: nothing of the warp's bookkeeping is carried across the exact pass.
+    int waited = 0;
+    const StepConst sc = StepConst::load_shared(sc_addr);
+    for (;;) {
 #pragma unroll
-    for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k) lane_update(f, L, mail);
-    if (STATS) ++n_iter;
-    const unsigned present = __reduce_or_sync(0xffffffffu, (unsigned)L.state);
-    const int todo = warp_decide(present, waited, f.resolve_wait);
-    if (todo == kWarpStep) continue;
-    if (todo == kWarpDone) break;  // every ray of the patch has ended
-    if (STATS) ++n_pass;
-    if (L.state & (kPend | kPendChord)) {
-      if (STATS) ++n_test;
-      lane_resolve(f, L, mail);
+      for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k) lane_update(f, L, mail, sc);
+      if (STATS) ++n_iter;
+      const unsigned present = __reduce_or_sync(0xffffffffu, (unsigned)L.state);
+      const int todo = warp_decide(present, waited, f.resolve_wait);
+      if (todo == kWarpStep) continue;
+      done = (todo == kWarpDone);  // every ray of the patch has ended
+      break;
     }
+    if (done) break;
+    if (STATS) {
+      ++n_pass;
+      if (L.state & (kPend | kPendChord)) ++n_test;
+    }
+#if defined(BH8_TRACE_X)
+    if (x == BH8_TRACE_X && y == BH8_TRACE_Y)
+      printf("pre-resolve: state %d idx %d k %u lo %d span %u inc %d next %d flags %d u %.6g phi %.6g\n", L.state, L.idx(), L.k, L.lo,
+             L.span, L.inc, mail.get_w(kMwNext), mail.get_w(kMwFlags), L.u, L.phi);
+#endif
+    lane_resolve(f, L, mail, fetch);  // all 32 lanes together; it colours the rays that end
+#if defined(BH8_TRACE_X)
+    if (x == BH8_TRACE_X && y == BH8_TRACE_Y)
+      printf("post-resolve: state %d idx %d k %u lo %d span %u inc %d next %d steps %d\n", L.state, L.idx(), L.k, L.lo,
+             L.span, L.inc, mail.get_w(kMwNext), mail.get_w(kMwSteps));
+#endif
   }
   const int steps = inside ? mail.get_w(kMwSteps) : 0;
   const int hit_obj = inside ? mail.get_w(kMwHit) : -1;
 
-  // ---- colour ------------------------------------------------------------------------------------
-  lane_shade(f, L, mail, hit_obj, DeviceFetch{tex});
-  const uint32_t bgr = L.bgr, oob = L.oob;
+  // ---- colour: lane_exact left it in the mailbox when the ray hit -----------------------------------
+  const uint32_t bgr = hit_obj >= 0 ? (uint32_t)mail.get_w(kMwBgr) : 0u;
+  const uint32_t oob = hit_obj >= 0 ? (uint32_t)mail.get_w(kMwOob) : 0u;
   int cls = BH8_CLASS_BACKGROUND, key = -1;
   if (hit_obj >= 0) {
     cls = f.obj[hit_obj].cls;

@@ -41,26 +41,26 @@ static void trace_frame(const Bh8Frame& f, const HostFetch& fetch, uint8_t* out_
   for (int y = 0; y < f.height; ++y) {
     for (int x = 0; x < f.width; ++x) {
       bh8::Lane<NN> L;
-      double md[bh8::kMailDoublesRay];
-      int32_t mw[bh8::kMailIntsRay];
+      double md[bh8::kMailDoubles];
+      int32_t mw[bh8::kMailInts];
       const bh8::Mail mail{md, mw, 1};
       bh8::lane_setup(f, x, y, L, mail);
+      bh8::lane_park_constants(L, mail);
       while (L.state != bh8::kDead) {  // the kernel's per-lane sequence, one lane, no batching
         if (L.state == bh8::kRun) {
           counters[0]++;
-          bh8::lane_update(f, L, mail);
+          bh8::lane_update(f, L, mail, bh8::StepConst::load(f));
         } else {
           // In the kernel a frozen lane keeps executing the warp's straight-line updates until the
           // warp attends to it: they must not change anything.
-          for (int k = 0; k < g_frozen_updates; ++k) bh8::lane_update(f, L, mail);
+          for (int k = 0; k < g_frozen_updates; ++k) bh8::lane_update(f, L, mail, bh8::StepConst::load(f));
           counters[1]++;
-          bh8::lane_exact(f, L, mail);
+          bh8::lane_resolve(f, L, mail, fetch);
         }
       }
-      for (int k = 0; k < g_frozen_updates; ++k) bh8::lane_update(f, L, mail);  // ended rays too
+      for (int k = 0; k < g_frozen_updates; ++k) bh8::lane_update(f, L, mail, bh8::StepConst::load(f));  // ended rays too
       const int hit_obj = mail.get_w(bh8::kMwHit);
-      bh8::lane_shade(f, L, mail, hit_obj, fetch);
-      const uint32_t bgr = L.bgr;
+      const uint32_t bgr = hit_obj >= 0 ? (uint32_t)mail.get_w(bh8::kMwBgr) : 0u;
       int cls = BH8_CLASS_BACKGROUND, key = -1;
       if (hit_obj >= 0) {
         cls = f.obj[hit_obj].cls;
@@ -180,8 +180,7 @@ extern "C" int bh8_harness_replay(const bh8_scene* scene0, const bh8_basis* basi
 // ---- a warp of the kernel, emulated ---------------------------------------------------------------
 // 32 lanes = one 8x4-pixel patch, stepped in lockstep exactly as render_tile (bh8_kernel.cuh) does it:
 // `updates_per_vote` straight-line updates for EVERY lane (frozen and dead ones included), the OR of
-// the lanes' states, bh8::warp_decide, and bh8::lane_resolve (park -> exact test on a copy -> unpark)
-// for the parked lanes -- the same functions the kernel inlines, with a mailbox laid out as in shared
+// the lanes' states, bh8::warp_decide, and bh8::lane_exact for ALL lanes (parked or not) -- the same functions the kernel inlines, with a mailbox laid out as in shared
 // memory (component c of lane l at [c * 32 + l]).  What the per-lane loop above cannot show -- lanes
 // waiting frozen while others travel, batched tests, the register parking -- is exercised here.
 template <int NN>
@@ -209,7 +208,7 @@ static void trace_frame_warps(const Bh8Frame& f, const HostFetch& fetch, int upd
       for (uint64_t round = 0;; ++round) {
         unsigned present = 0;
         for (int l = 0; l < kLanes; ++l) {
-          for (int k = 0; k < updates_per_vote; ++k) bh8::lane_update(f, L[l], mail[l]);
+          for (int k = 0; k < updates_per_vote; ++k) bh8::lane_update(f, L[l], mail[l], bh8::StepConst::load(f));
           present |= (unsigned)L[l].state;
         }
         counters[0] += (uint64_t)updates_per_vote;  // update slots of this warp
@@ -217,16 +216,14 @@ static void trace_frame_warps(const Bh8Frame& f, const HostFetch& fetch, int upd
         if (todo == bh8::kWarpStep) continue;
         if (todo == bh8::kWarpDone) break;
         counters[1]++;  // resolve passes
-        for (int l = 0; l < kLanes; ++l)
-          if (L[l].state & (bh8::kPend | bh8::kPendChord)) bh8::lane_resolve(f, L[l], mail[l]);
+        for (int l = 0; l < kLanes; ++l) bh8::lane_resolve(f, L[l], mail[l], fetch);  // ALL lanes, as in the kernel
         if (round > 100000000ull) return;  // a warp that never ends would hang the GPU: leave zeros, the test fails
       }
       for (int l = 0; l < kLanes; ++l) {
         if (!inside[l]) continue;
         const int x = px0 + (l % kPW), y = py0 + (l / kPW);
         const int hit_obj = mail[l].get_w(bh8::kMwHit);
-        bh8::lane_shade(f, L[l], mail[l], hit_obj, fetch);
-        const uint32_t bgr = L[l].bgr;
+        const uint32_t bgr = hit_obj >= 0 ? (uint32_t)mail[l].get_w(bh8::kMwBgr) : 0u;
         const size_t i = static_cast<size_t>(y) * f.width + x;
         out_bgr[3 * i] = bgr & 255;
         out_bgr[3 * i + 1] = (bgr >> 8) & 255;
