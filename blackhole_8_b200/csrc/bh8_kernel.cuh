@@ -56,8 +56,12 @@ struct Bh8Out {
   uint16_t* steps;
   unsigned long long* stats;  // [0] rays [1] steps [2..5] class counts [6] tex_oob [7] warps [8] update slots
                               // [9] resolve passes [10] exact tests (see bh8_stats)
-  int32_t vec_ok;             // 16-byte row stores are legal: 4-byte formats width % 4 == 0, BGR8 width % 32 == 0;
-                              // base 16-byte aligned
+  int32_t vec_ok;             // (linear kernel) 16-byte row stores are legal: 4-byte formats width % 4 == 0, BGR8
+                              // width % 32 == 0; base 16-byte aligned
+  // persistent-warp scheduling of the geodesic kernel (render_warps): ticket counter + leavers, both zero
+  // between launches; the frame as tiles of 32x8 pixels, 8 patches each
+  unsigned* sched;
+  int32_t tiles_x, n_patches;
 };
 constexpr int kStatSlots = 11;
 
@@ -149,10 +153,87 @@ __device__ __forceinline__ void store_pixel(const Bh8Frame& f, const Bh8Out& out
   }
 }
 
-// One 32x8 tile of the frame.  `f` is a __grid_constant__ kernel parameter, i.e. in the constant bank:
-// its fields are direct operands of the FP64 instructions.
+// ---- the geodesic kernel ------------------------------------------------------------------------------
+// `f` is a __grid_constant__ kernel parameter, i.e. in the constant bank: its fields are direct operands
+// of the FP64 instructions.
 // STATS: the instantiation BH8_FLAG_STATS launches take -- it also counts the warp schedule (update slots,
 // resolve passes, exact tests); the plain one carries no counter through the stepping loop.
+
+struct SchedCount {
+  unsigned n_iter = 0, n_pass = 0, n_test = 0;
+};
+
+// One 8x4-pixel patch, all 32 lanes of the warp: ray setup, then stepping phases and exact passes in turn
+// until every ray of the patch has ended.  The result waits in each lane's mailbox (kMwSteps, kMwHit,
+// kMwBgr, kMwOob).
+template <int NN, bool STATS>
+__device__ __forceinline__ void trace_patch(const Bh8Frame& f, const DeviceFetch& fetch, const Mail mail,
+                                            uint32_t sc_addr, int x, int y, bool inside, SchedCount& sc_n) {
+  Lane<NN> L;
+  lane_inert(L);
+  if (inside) {
+    lane_setup(f, x, y, L, mail);
+    lane_park_constants(L, mail);
+  }
+  for (bool done = false; !done;) {
+    // Lean stepping: the same straight-line update for every lane (frozen lanes are inert, see
+    // lane_freeze), a few updates per round of warp votes, until the warp decides to attend to its
+    // parked lanes (or every ray has ended).  `waited` and the update's constants live in this phase
+    // only: nothing of the warp's bookkeeping is carried across the exact pass.
+    int waited = 0;
+    const StepConst sc = StepConst::load_shared(sc_addr);
+    for (;;) {
+#if defined(BH8_SINGLE_UPDATE_COPY)  // A/B: one copy of the update (and of its rare path) in the instruction stream
+#pragma unroll 1
+      for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k) lane_update(f, L, mail, sc);
+#else
+#pragma unroll
+      for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k) lane_update(f, L, mail, sc);
+#endif
+      if (STATS) ++sc_n.n_iter;
+      const unsigned present = __reduce_or_sync(0xffffffffu, (unsigned)L.state);
+      const int todo = warp_decide(present, waited, f.resolve_wait);
+      if (todo == kWarpStep) continue;
+      done = (todo == kWarpDone);  // every ray of the patch has ended
+      break;
+    }
+    if (done) break;
+    if (STATS) {
+      ++sc_n.n_pass;
+      if (L.state & (kPend | kPendChord)) ++sc_n.n_test;
+    }
+    lane_resolve(f, L, mail, fetch);  // all 32 lanes together; it colours the rays that end
+  }
+}
+
+// Mailbox of this thread + the warp's copy of the stepping constants (StepConst) in shared memory.
+__device__ __forceinline__ Mail make_mail(const Bh8Frame& f, int tid, int lane, int warp, uint32_t* sc_addr) {
+  __shared__ double sh_md[kMailDoubles * kThreads];
+  __shared__ int sh_mi[kMailInts * kThreads];
+  __shared__ double sh_step_const[kThreads / 32][2];
+  Mail mail;
+#if defined(__CUDA_ARCH__)
+  mail.d = (uint32_t)__cvta_generic_to_shared(sh_md + tid);
+  mail.w = (uint32_t)__cvta_generic_to_shared(sh_mi + tid);
+  asm volatile("" : "+r"(mail.d), "+r"(mail.w));  // opaque: two registers, never re-derived
+#else
+  mail.d = sh_md + tid;  // (nvcc's host pass only parses this)
+  mail.w = sh_mi + tid;
+#endif
+  mail.stride = kThreads;
+  // The two FP64 constants of the geodesic update (2M, 3/8) go through shared memory once per warp so
+  // that the stepping loop holds them in registers: see StepConst.
+  if (lane == 0) {
+    sh_step_const[warp][0] = f.two_m;
+    sh_step_const[warp][1] = 0.375;
+  }
+  __syncwarp();
+  *sc_addr = (uint32_t)__cvta_generic_to_shared(&sh_step_const[warp][0]);
+  return mail;
+}
+
+#if !defined(BH8_PERSISTENT_WARPS)
+// One 32x8 tile of the frame per CTA; a warp is one 8x4 patch of it.
 template <int NN, bool STATS>
 __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex, const Bh8Out& out) {
   __shared__ __align__(16) uint32_t sh_rgba[kThreads];
@@ -180,74 +261,15 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
   const int x = x0 + px, y = y0 + py;
   const bool inside = x < f.width && y < f.height;
 
-  // ---- trace ----------------------------------------------------------------------------------
-  __shared__ double sh_md[kMailDoubles * kThreads];
-  __shared__ int sh_mi[kMailInts * kThreads];
-  Mail mail;
-#if defined(__CUDA_ARCH__)
-  mail.d = (uint32_t)__cvta_generic_to_shared(sh_md + tid);
-  mail.w = (uint32_t)__cvta_generic_to_shared(sh_mi + tid);
-  asm volatile("" : "+r"(mail.d), "+r"(mail.w));  // opaque: two registers, never re-derived
-#else
-  mail.d = sh_md + tid;  // (nvcc's host pass only parses this)
-  mail.w = sh_mi + tid;
-#endif
-  mail.stride = kThreads;
-  Lane<NN> L;
-  lane_inert(L);
-  if (inside) {
-    lane_setup(f, x, y, L, mail);
-    lane_park_constants(L, mail);
-  }
+  uint32_t sc_addr;
+  const Mail mail = make_mail(f, tid, lane, warp, &sc_addr);
   const DeviceFetch fetch{tex};
-  // The two FP64 constants of the geodesic update (2M, 3/8) go through shared memory once per warp so
-  // that the stepping loop holds them in registers: see StepConst.
-  __shared__ double sh_step_const[kThreads / 32][2];
-  if (lane == 0) {
-    sh_step_const[warp][0] = f.two_m;
-    sh_step_const[warp][1] = 0.375;
-  }
-  __syncwarp();
-  const uint32_t sc_addr = (uint32_t)__cvta_generic_to_shared(&sh_step_const[warp][0]);
-  unsigned n_iter = 0, n_pass = 0, n_test = 0;
-  for (bool done = false; !done;) {
-    // Lean stepping: the same straight-line update for every lane (frozen lanes are inert, see
-    // lane_freeze), a few updates per round of warp votes, until the warp decides to attend to its
-    // parked lanes (or every ray has ended).  `waited` and the update's constants live in this phase
-    // only: nothing of the warp's bookkeeping is carried across the exact pass.
-    int waited = 0;
-    const StepConst sc = StepConst::load_shared(sc_addr);
-    for (;;) {
-#pragma unroll
-      for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k) lane_update(f, L, mail, sc);
-      if (STATS) ++n_iter;
-      const unsigned present = __reduce_or_sync(0xffffffffu, (unsigned)L.state);
-      const int todo = warp_decide(present, waited, f.resolve_wait);
-      if (todo == kWarpStep) continue;
-      done = (todo == kWarpDone);  // every ray of the patch has ended
-      break;
-    }
-    if (done) break;
-    if (STATS) {
-      ++n_pass;
-      if (L.state & (kPend | kPendChord)) ++n_test;
-    }
-#if defined(BH8_TRACE_X)
-    if (x == BH8_TRACE_X && y == BH8_TRACE_Y)
-      printf("pre-resolve: state %d idx %d k %u lo %d span %u inc %d next %d flags %d u %.6g phi %.6g\n", L.state, L.idx(), L.k, L.lo,
-             L.span, L.inc, mail.get_w(kMwNext), mail.get_w(kMwFlags), L.u, L.phi);
-#endif
-    lane_resolve(f, L, mail, fetch);  // all 32 lanes together; it colours the rays that end
-#if defined(BH8_TRACE_X)
-    if (x == BH8_TRACE_X && y == BH8_TRACE_Y)
-      printf("post-resolve: state %d idx %d k %u lo %d span %u inc %d next %d steps %d\n", L.state, L.idx(), L.k, L.lo,
-             L.span, L.inc, mail.get_w(kMwNext), mail.get_w(kMwSteps));
-#endif
-  }
-  const int steps = inside ? mail.get_w(kMwSteps) : 0;
-  const int hit_obj = inside ? mail.get_w(kMwHit) : -1;
+  SchedCount n;
+  trace_patch<NN, STATS>(f, fetch, mail, sc_addr, x, y, inside, n);
 
   // ---- colour: lane_exact left it in the mailbox when the ray hit -----------------------------------
+  const int steps = inside ? mail.get_w(kMwSteps) : 0;
+  const int hit_obj = inside ? mail.get_w(kMwHit) : -1;
   const uint32_t bgr = hit_obj >= 0 ? (uint32_t)mail.get_w(kMwBgr) : 0u;
   const uint32_t oob = hit_obj >= 0 ? (uint32_t)mail.get_w(kMwOob) : 0u;
   int cls = BH8_CLASS_BACKGROUND, key = -1;
@@ -255,8 +277,28 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
     cls = f.obj[hit_obj].cls;
     key = f.obj[hit_obj].key;
   }
+  // Plain launches (no maps, no counters): every warp stores its own patch the moment it is done -- four
+  // 32-byte row segments for the 4-byte formats, 24-byte ones for BGR8 -- and leaves; no CTA barrier, no
+  // staging tile (+1.5 % over the tile path on B200, which the launches with maps / counters still take).
+  if (!STATS && !out.cls && !out.key && !out.steps) {
+    if (inside) {
+      const size_t gi = (size_t)y * f.width + x;
+      if (f.pixel_format == BH8_PIXEL_BGR8) {
+        uint8_t* d = out.pixels + gi * 3;
+        d[0] = (uint8_t)bgr;
+        d[1] = (uint8_t)(bgr >> 8);
+        d[2] = (uint8_t)(bgr >> 16);
+      } else {
+        const uint32_t px4 = (f.pixel_format == BH8_PIXEL_BGRA8)
+                                 ? (bgr | 0xFF000000u)
+                                 : (((bgr >> 16) & 0xFFu) | (bgr & 0xFF00u) | ((bgr & 0xFFu) << 16) | 0xFF000000u);
+        reinterpret_cast<uint32_t*>(out.pixels)[gi] = px4;
+      }
+    }
+    return;
+  }
   store_pixel(f, out, sh_rgba, sh_red, tid, lane, slot, x0, y0, x, y, inside, bgr, oob, cls, key, steps,
-              n_iter * BH8_UPDATES_PER_VOTE, n_pass, n_test);
+              n.n_iter * BH8_UPDATES_PER_VOTE, n.n_pass, n.n_test);
 }
 
 template <int NN, bool STATS>
@@ -264,6 +306,117 @@ __global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
 bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
   render_tile<NN, STATS>(f, tex, out);
 }
+
+#else  // BH8_PERSISTENT_WARPS
+// A/B VARIANT, not the shipped configuration (profiles/r02_refill_ab.json): persistent
+// warps.  The grid is one wave of CTAs (SMs x BH8_MIN_BLOCKS); every warp draws 8x4-pixel patches from a
+// device-wide ticket counter (out.sched[0]) until the frame has none left, so no warp slot idles while
+// the slowest warp of a CTA finishes and the tail of the frame is one patch long.  Patches are numbered
+// tile by tile.  The warp that leaves last resets the counters (out.sched[1] counts leavers).  Measured
+// on B200: 8 % SLOWER at 1080p / nstep 20 (warps of a CTA no longer run the same phase at the same time),
+// 1.5 % faster at 8K / nstep 200.
+template <int NN, bool STATS>
+__device__ __forceinline__ void render_warps(const Bh8Frame& f, const Bh8Tex& tex, const Bh8Out& out) {
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  uint32_t sc_addr;
+  const Mail mail = make_mail(f, tid, lane, warp, &sc_addr);
+  const DeviceFetch fetch{tex};
+
+  // per-warp totals for the optional counters (added to out.stats once, when the warp leaves)
+  unsigned long long st_rays = 0, st_steps = 0, st_oob = 0, st_cls0 = 0, st_cls1 = 0, st_cls2 = 0, st_cls3 = 0;
+  unsigned st_patches = 0;
+  SchedCount n;
+
+  constexpr int kPatchesPerTile = kPatchesAcross * (kTileH / kPatchH);
+  for (;;) {
+    unsigned patch = 0;
+    if (lane == 0) patch = atomicAdd(out.sched, 1u);
+    patch = __shfl_sync(0xffffffffu, patch, 0);
+    if (patch >= (unsigned)out.n_patches) break;
+    const int tile = (int)(patch / kPatchesPerTile), sub = (int)(patch % kPatchesPerTile);
+    const int ty = tile / out.tiles_x, tx = tile - ty * out.tiles_x;
+    const int x0 = tx * kTileW;
+    int y0;  // ty counts tile rows of THIS shard's stripes
+    if (f.shard_count > 1) {
+      const int tiles_per_stripe = f.stripe_rows / kTileH;
+      const int ls = ty / tiles_per_stripe;
+      const int within = ty - ls * tiles_per_stripe;
+      y0 = (ls * f.shard_count + f.shard_index) * f.stripe_rows + within * kTileH;
+    } else {
+      y0 = ty * kTileH;
+    }
+    const int x = x0 + (sub % kPatchesAcross) * kPatchW + (lane % kPatchW);
+    const int y = y0 + (sub / kPatchesAcross) * kPatchH + (lane / kPatchW);
+    const bool inside = x < f.width && y < f.height;
+    if (STATS) ++st_patches;
+    trace_patch<NN, STATS>(f, fetch, mail, sc_addr, x, y, inside, n);
+
+    if (inside) {  // a warp stores its own patch: four 32-byte row segments (4-byte formats)
+      const int steps = mail.get_w(kMwSteps);
+      const int hit_obj = mail.get_w(kMwHit);
+      const uint32_t bgr = hit_obj >= 0 ? (uint32_t)mail.get_w(kMwBgr) : 0u;
+      int cls = BH8_CLASS_BACKGROUND, key = -1;
+      if (hit_obj >= 0) {
+        cls = f.obj[hit_obj].cls;
+        key = f.obj[hit_obj].key;
+      }
+      const size_t gi = (size_t)y * f.width + x;
+      if (f.pixel_format == BH8_PIXEL_BGR8) {
+        uint8_t* d = out.pixels + gi * 3;
+        d[0] = (uint8_t)bgr;
+        d[1] = (uint8_t)(bgr >> 8);
+        d[2] = (uint8_t)(bgr >> 16);
+      } else {
+        const uint32_t px4 = (f.pixel_format == BH8_PIXEL_BGRA8)
+                                 ? (bgr | 0xFF000000u)
+                                 : (((bgr >> 16) & 0xFFu) | (bgr & 0xFF00u) | ((bgr & 0xFFu) << 16) | 0xFF000000u);
+        reinterpret_cast<uint32_t*>(out.pixels)[gi] = px4;
+      }
+      if (out.cls) out.cls[gi] = (uint8_t)cls;
+      if (out.key) out.key[gi] = (int8_t)key;
+      if (out.steps) out.steps[gi] = (uint16_t)steps;
+      if (STATS) {
+        ++st_rays;
+        st_steps += (unsigned)steps;
+        st_oob += hit_obj >= 0 ? (uint32_t)mail.get_w(kMwOob) : 0u;
+        st_cls0 += cls == 0;
+        st_cls1 += cls == 1;
+        st_cls2 += cls == 2;
+        st_cls3 += cls == 3;
+      }
+    }
+  }
+  if (STATS) {
+    unsigned long long v[kStatSlots] = {st_rays, st_steps, st_cls0, st_cls1, st_cls2, st_cls3, st_oob,
+                                        lane == 0 ? st_patches : 0ull,
+                                        lane == 0 ? (unsigned long long)n.n_iter * BH8_UPDATES_PER_VOTE : 0ull,
+                                        lane == 0 ? n.n_pass : 0ull, n.n_test};
+#pragma unroll
+    for (int k = 0; k < kStatSlots; ++k) {
+      unsigned long long t = v[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0 && t) atomicAdd(&out.stats[k], t);
+    }
+  }
+  if (lane == 0) {
+    __threadfence();
+    const unsigned total = gridDim.x * (kThreads / 32);
+    if (atomicAdd(out.sched + 1, 1u) == total - 1u) {  // every warp has made its last (failing) draw
+      out.sched[0] = 0u;
+      out.sched[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+template <int NN, bool STATS>
+__global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
+bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
+  render_warps<NN, STATS>(f, tex, out);
+}
+#endif  // BH8_PERSISTENT_WARPS
 
 // Flat-space tracer (BH8_TRACER_LINEAR): one thread per pixel, at most linear_steps segment tests,
 // same tile mapping, colour and store path as the geodesic kernel.

@@ -31,6 +31,14 @@ struct Device {
   cudaArray_t tex_array[BH8_MAX_TEXTURES] = {};
   cudaTextureObject_t tex_obj[BH8_MAX_TEXTURES] = {};
   unsigned long long* d_stats = nullptr;  // 16 counters (bh8::kStatSlots used)
+  // Ticket counters of the persistent-warp render kernel (bh8::render_warps): one pair per stream that
+  // launches it (kernels on different streams of one device may overlap), each pair on its own 128-byte line.
+  // The kernel leaves them zero.
+  static constexpr int kSchedSlots = 16, kSchedStride = 32;
+  unsigned* d_sched = nullptr;
+  cudaStream_t sched_stream[kSchedSlots] = {};
+  int n_sched = 0;
+  int sm_count = 0;
   // double-buffered frame staging for bh8_render()
   void* d_pix[2] = {nullptr, nullptr};
   uint8_t* d_cls[2] = {nullptr, nullptr};
@@ -117,6 +125,9 @@ int launch_built(bh8_ctx* ctx, Device& d, Bh8Frame& f, void* d_pixels, void* d_c
   const bool aligned = reinterpret_cast<uintptr_t>(d_pixels) % 16 == 0;
   out.vec_ok = aligned && (f.pixel_format == BH8_PIXEL_BGR8 ? f.width % 32 == 0 : f.width % 4 == 0);
   BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  out.sched = nullptr;
+  out.tiles_x = static_cast<int32_t>(grid.x);
+  out.n_patches = static_cast<int32_t>(grid.x * grid.y * (bh8::kTileW / bh8::kPatchW) * (bh8::kTileH / bh8::kPatchH));
   if (f.tracer == BH8_TRACER_LINEAR) {
     bh8::bh8_linear_kernel<<<grid, bh8::kThreads, 0, st>>>(f, tex, out);
     BH8_CUDA(ctx, cudaGetLastError());
@@ -127,6 +138,22 @@ int launch_built(bh8_ctx* ctx, Device& d, Bh8Frame& f, void* d_pixels, void* d_c
   // planes than filter slots take the generic instantiation (exact test on every gated step).
   // BH8_FLAG_STATS launches take the instantiation that also counts the warp schedule.
   const int nn = f.n_nc <= bh8::kMaxFilterPlanes ? f.n_nc : -1;
+  // Persistent warps: one wave of CTAs, every warp draws 8x4-pixel patches from the stream's ticket counter.
+  {
+    int slot = -1;
+    for (int i = 0; i < d.n_sched; ++i)
+      if (d.sched_stream[i] == st) slot = i;
+    if (slot < 0) {
+      if (d.n_sched == Device::kSchedSlots) return fail(ctx, BH8_EINVAL, "too many streams render on one device");
+      slot = d.n_sched++;
+      d.sched_stream[slot] = st;
+    }
+    out.sched = d.d_sched + slot * Device::kSchedStride;
+  }
+#if defined(BH8_PERSISTENT_WARPS)  // A/B variant: one wave of CTAs, patches drawn from the ticket counter
+  const unsigned tiles = grid.x * grid.y, wave = static_cast<unsigned>(d.sm_count) * BH8_MIN_BLOCKS;
+  grid = dim3(tiles < wave ? tiles : wave, 1, 1);
+#endif
 #define BH8_LAUNCH(NN_)                                                                    \
   do {                                                                                     \
     if (f.flags & BH8_FLAG_STATS)                                                          \
@@ -266,6 +293,10 @@ int bh8_create(bh8_ctx** out, const int* devices, int n_dev) {
     for (int b = 0; b < 2; ++b) BH8_CREATE_CUDA(cudaStreamCreateWithFlags(&d.slot_stream[b], cudaStreamNonBlocking));
     BH8_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.d_stats), 16 * sizeof(unsigned long long)));
     BH8_CREATE_CUDA(cudaMemset(d.d_stats, 0, 16 * sizeof(unsigned long long)));
+    d.sm_count = prop.multiProcessorCount;
+    BH8_CREATE_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.d_sched),
+                               Device::kSchedSlots * Device::kSchedStride * sizeof(unsigned)));
+    BH8_CREATE_CUDA(cudaMemset(d.d_sched, 0, Device::kSchedSlots * Device::kSchedStride * sizeof(unsigned)));
     for (int b = 0; b < 2; ++b) {
       BH8_CREATE_CUDA(cudaEventCreateWithFlags(&d.ev_kernel_done[b], cudaEventDisableTiming));
       BH8_CREATE_CUDA(cudaEventCreateWithFlags(&d.ev_copy_done[b], cudaEventDisableTiming));
@@ -311,6 +342,7 @@ void bh8_destroy(bh8_ctx* ctx) {
     if (d.ev_t0) cudaEventDestroy(d.ev_t0);
     if (d.ev_t1) cudaEventDestroy(d.ev_t1);
     cudaFree(d.d_stats);
+    cudaFree(d.d_sched);
     if (i == 0)
       for (void* p : ctx->owned) cudaFree(p);
     if (d.stream) cudaStreamDestroy(d.stream);
