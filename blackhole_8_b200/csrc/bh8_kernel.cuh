@@ -38,9 +38,7 @@ constexpr int kThreads = kTileW * kTileH;
 constexpr int kPatchW = BH8_PATCH_W, kPatchH = 32 / BH8_PATCH_W, kPatchesAcross = kTileW / kPatchW;
 static_assert(kPatchW * kPatchH == 32 && kTileH % kPatchH == 0, "a warp must tile the CTA's pixels");
 constexpr int kMaxFilterPlanes = kMaxFilterSlots;
-#ifndef BH8_UPDATES_PER_VOTE
-#define BH8_UPDATES_PER_VOTE 2  // geodesic updates between two rounds of warp votes
-#endif
+constexpr int kFineNstep = 64;  // from here on the kernel takes 3 updates per round of votes instead of 2
 #ifndef BH8_MIN_BLOCKS
 #define BH8_MIN_BLOCKS 5  // CTAs per SM the register allocation is sized for (measured best of 2..5 on B200)
 #endif
@@ -166,7 +164,7 @@ struct SchedCount {
 // One 8x4-pixel patch, all 32 lanes of the warp: ray setup, then stepping phases and exact passes in turn
 // until every ray of the patch has ended.  The result waits in each lane's mailbox (kMwSteps, kMwHit,
 // kMwBgr, kMwOob).
-template <int NN, bool STATS>
+template <int NN, bool STATS, int UPV>
 __device__ __forceinline__ void trace_patch(const Bh8Frame& f, const DeviceFetch& fetch, const Mail mail,
                                             uint32_t sc_addr, int x, int y, bool inside, SchedCount& sc_n) {
   Lane<NN> L;
@@ -183,13 +181,8 @@ __device__ __forceinline__ void trace_patch(const Bh8Frame& f, const DeviceFetch
     int waited = 0;
     const StepConst sc = StepConst::load_shared(sc_addr);
     for (;;) {
-#if defined(BH8_SINGLE_UPDATE_COPY)  // A/B: one copy of the update (and of its rare path) in the instruction stream
-#pragma unroll 1
-      for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k) lane_update(f, L, mail, sc);
-#else
 #pragma unroll
-      for (int k = 0; k < BH8_UPDATES_PER_VOTE; ++k) lane_update(f, L, mail, sc);
-#endif
+      for (int k = 0; k < UPV; ++k) lane_update(f, L, mail, sc);
       if (STATS) ++sc_n.n_iter;
       const unsigned present = __reduce_or_sync(0xffffffffu, (unsigned)L.state);
       const int todo = warp_decide(present, waited, f.resolve_wait);
@@ -233,8 +226,10 @@ __device__ __forceinline__ Mail make_mail(const Bh8Frame& f, int tid, int lane, 
 }
 
 #if !defined(BH8_PERSISTENT_WARPS)
-// One 32x8 tile of the frame per CTA; a warp is one 8x4 patch of it.
-template <int NN, bool STATS>
+// One 32x8 tile of the frame per CTA; a warp is one 8x4 patch of it.  UPV: geodesic updates between two
+// rounds of warp votes -- 2 for the reference's nstep 20, 3 for fine steps (nstep >= 64: lanes drift apart
+// more slowly relative to the length of a ray; measured +2.4 % at 8K / nstep 200, -1.3 % at nstep 20).
+template <int NN, bool STATS, int UPV>
 __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex, const Bh8Out& out) {
   __shared__ __align__(16) uint32_t sh_rgba[kThreads];
   __shared__ unsigned long long sh_red[kStatSlots];
@@ -265,7 +260,7 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
   const Mail mail = make_mail(f, tid, lane, warp, &sc_addr);
   const DeviceFetch fetch{tex};
   SchedCount n;
-  trace_patch<NN, STATS>(f, fetch, mail, sc_addr, x, y, inside, n);
+  trace_patch<NN, STATS, UPV>(f, fetch, mail, sc_addr, x, y, inside, n);
 
   // ---- colour: lane_exact left it in the mailbox when the ray hit -----------------------------------
   const int steps = inside ? mail.get_w(kMwSteps) : 0;
@@ -298,13 +293,13 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
     return;
   }
   store_pixel(f, out, sh_rgba, sh_red, tid, lane, slot, x0, y0, x, y, inside, bgr, oob, cls, key, steps,
-              n.n_iter * BH8_UPDATES_PER_VOTE, n.n_pass, n.n_test);
+              n.n_iter * UPV, n.n_pass, n.n_test);
 }
 
-template <int NN, bool STATS>
+template <int NN, bool STATS, int UPV>
 __global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
 bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
-  render_tile<NN, STATS>(f, tex, out);
+  render_tile<NN, STATS, UPV>(f, tex, out);
 }
 
 #else  // BH8_PERSISTENT_WARPS
@@ -315,7 +310,7 @@ bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
 // tile by tile.  The warp that leaves last resets the counters (out.sched[1] counts leavers).  Measured
 // on B200: 8 % SLOWER at 1080p / nstep 20 (warps of a CTA no longer run the same phase at the same time),
 // 1.5 % faster at 8K / nstep 200.
-template <int NN, bool STATS>
+template <int NN, bool STATS, int UPV>
 __device__ __forceinline__ void render_warps(const Bh8Frame& f, const Bh8Tex& tex, const Bh8Out& out) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -350,7 +345,7 @@ __device__ __forceinline__ void render_warps(const Bh8Frame& f, const Bh8Tex& te
     const int y = y0 + (sub / kPatchesAcross) * kPatchH + (lane / kPatchW);
     const bool inside = x < f.width && y < f.height;
     if (STATS) ++st_patches;
-    trace_patch<NN, STATS>(f, fetch, mail, sc_addr, x, y, inside, n);
+    trace_patch<NN, STATS, UPV>(f, fetch, mail, sc_addr, x, y, inside, n);
 
     if (inside) {  // a warp stores its own patch: four 32-byte row segments (4-byte formats)
       const int steps = mail.get_w(kMwSteps);
@@ -390,7 +385,7 @@ __device__ __forceinline__ void render_warps(const Bh8Frame& f, const Bh8Tex& te
   if (STATS) {
     unsigned long long v[kStatSlots] = {st_rays, st_steps, st_cls0, st_cls1, st_cls2, st_cls3, st_oob,
                                         lane == 0 ? st_patches : 0ull,
-                                        lane == 0 ? (unsigned long long)n.n_iter * BH8_UPDATES_PER_VOTE : 0ull,
+                                        lane == 0 ? (unsigned long long)n.n_iter * UPV : 0ull,
                                         lane == 0 ? n.n_pass : 0ull, n.n_test};
 #pragma unroll
     for (int k = 0; k < kStatSlots; ++k) {
@@ -411,10 +406,10 @@ __device__ __forceinline__ void render_warps(const Bh8Frame& f, const Bh8Tex& te
   }
 }
 
-template <int NN, bool STATS>
+template <int NN, bool STATS, int UPV>
 __global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
 bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
-  render_warps<NN, STATS>(f, tex, out);
+  render_warps<NN, STATS, UPV>(f, tex, out);
 }
 #endif  // BH8_PERSISTENT_WARPS
 

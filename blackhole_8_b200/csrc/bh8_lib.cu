@@ -154,12 +154,19 @@ int launch_built(bh8_ctx* ctx, Device& d, Bh8Frame& f, void* d_pixels, void* d_c
   const unsigned tiles = grid.x * grid.y, wave = static_cast<unsigned>(d.sm_count) * BH8_MIN_BLOCKS;
   grid = dim3(tiles < wave ? tiles : wave, 1, 1);
 #endif
+#define BH8_LAUNCH2(NN_, ST_)                                                              \
+  do {                                                                                     \
+    if (f.nstep >= bh8::kFineNstep)                                                        \
+      bh8::bh8_render_kernel<NN_, ST_, 3><<<grid, bh8::kThreads, 0, st>>>(f, tex, out);    \
+    else                                                                                   \
+      bh8::bh8_render_kernel<NN_, ST_, 2><<<grid, bh8::kThreads, 0, st>>>(f, tex, out);    \
+  } while (0)
 #define BH8_LAUNCH(NN_)                                                                    \
   do {                                                                                     \
     if (f.flags & BH8_FLAG_STATS)                                                          \
-      bh8::bh8_render_kernel<NN_, true><<<grid, bh8::kThreads, 0, st>>>(f, tex, out);      \
+      BH8_LAUNCH2(NN_, true);                                                              \
     else                                                                                   \
-      bh8::bh8_render_kernel<NN_, false><<<grid, bh8::kThreads, 0, st>>>(f, tex, out);     \
+      BH8_LAUNCH2(NN_, false);                                                             \
   } while (0)
   switch (nn) {
     case 0: BH8_LAUNCH(0); break;
@@ -170,6 +177,7 @@ int launch_built(bh8_ctx* ctx, Device& d, Bh8Frame& f, void* d_pixels, void* d_c
     default: BH8_LAUNCH(-1); break;
   }
 #undef BH8_LAUNCH
+#undef BH8_LAUNCH2
   BH8_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
   return BH8_OK;

@@ -48,7 +48,7 @@ def main():
     src_csv, so, warps = sys.argv[1], sys.argv[2], float(sys.argv[3])
     nn = sys.argv[4] if len(sys.argv) > 4 else "1"
     top = int(sys.argv[5]) if len(sys.argv) > 5 else 25
-    tag = "bh8_render_kernelILi%sELb0E" % nn
+    tag = "bh8_render_kernelILi%sELb0ELi2E" % nn
     rows = list(csv.reader(open(src_csv)))
     hdr, executed, samples = None, {}, {}
     for r in rows:

@@ -18,7 +18,7 @@ def load(so, nn):
     ins, on = [], False
     for line in txt.splitlines():
         if "Function :" in line:
-            on = ("bh8_render_kernelILi%sELb0E" % nn) in line
+            on = ("bh8_render_kernelILi%sELb0ELi2E" % nn) in line
             continue
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
         if on and m:

@@ -29,7 +29,7 @@ def main():
     so = sys.argv[1]
     nn = sys.argv[2] if len(sys.argv) > 2 else "1"
     top_n = int(sys.argv[3]) if len(sys.argv) > 3 else 30
-    tag = "bh8_render_kernelILi%sELb0E" % nn if not nn.startswith("-") else "bh8_render_kernelILin%sELb0E" % nn[1:]
+    tag = "bh8_render_kernelILi%sELb0ELi2E" % nn if not nn.startswith("-") else "bh8_render_kernelILin%sELb0ELi2E" % nn[1:]
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=td, check=True, capture_output=True)
         cubin = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
