@@ -211,7 +211,8 @@ def run_reference_cpu(snap_name, frames, threads, frame=0):
 
 def measure_sink(r, my_frames, W, H, world=1, rank=0, frames=120, quality=95):
     """SURVEY 8f-2, reported beside the headline: frames/s of the GPU frame sink (bh8_sink_render: trace the
-    frame, JPEG-encode it on the device with nvJPEG, only the bitstream comes to the host) -- what the
+    frame, draw the reference's HUD text into it and JPEG-encode it on the device with this repo's own kernels
+    (csrc/bh8_jpeg.cuh), only the bitstream comes to the host) -- what the
     reference's `out_capture.write(frame)` becomes -- next to OpenCV's own JPEG encoder on one host core,
     which is what cv::VideoWriter(MJPG) spends per frame.  One sink per rank / GPU on that rank's frames;
     whole-job rate = world * frames / (max over ranks of the wall time).  Not part of value / e2e."""
@@ -223,6 +224,7 @@ def measure_sink(r, my_frames, W, H, world=1, rank=0, frames=120, quality=95):
         from blackhole_8_b200 import abi
         from blackhole_8_b200.renderer import VideoSink
         sink = VideoSink(r, None, W, H, fps=29, quality=quality)
+        sink.hud(abi.reference_hud(my_frames[0].camera))  # blackhole_solution_test.cc:309-326, drawn before the encode
         for i in range(5):
             sink.render(my_frames[i % len(my_frames)])
         before = sink.stats()
@@ -251,6 +253,9 @@ def measure_sink(r, my_frames, W, H, world=1, rank=0, frames=120, quality=95):
                "encode_ms": st["encode_ms"] - before["encode_ms"]}
         if rank == 0:
             frame = r.render(my_frames[(frames - 1) % len(my_frames)], pixel_format=abi.PIXEL_BGR8)["pixels"][0]
+            frame = np.ascontiguousarray(frame)
+            for text, x, y in abi.reference_hud(my_frames[0].camera):
+                cv2.putText(frame, text, (x, y), cv2.FONT_HERSHEY_PLAIN, 1, (0, 255, 0), 1)
             dec = cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_COLOR)
             mse = float(np.mean((dec.astype(np.float64) - frame.astype(np.float64)) ** 2))
             n_cpu = 8
@@ -276,14 +281,14 @@ def measure_sink(r, my_frames, W, H, world=1, rank=0, frames=120, quality=95):
     if err or ok_all < 1.0:
         return {"unavailable": err or "a rank failed"}
     n = out["n"]
-    return {"what": "bh8_sink_render: render + nvJPEG encode (4:2:0, quality %d) on the GPU, bitstream to host; "
-                    "one sink per GPU" % quality,
+    return {"what": "bh8_sink_render: render + HUD text + baseline JPEG encode (own kernels, 4:2:0, quality %d, restart "
+                    "interval 2 MCUs) on the GPU, bitstream to host; one sink per GPU" % quality,
             "frames_per_s": world * n / dt_max, "Mrays_per_s": world * n * W * H / dt_max / 1e6,
             "pipelined_bh8_sink_submit": {"frames_per_s": world * n / dt_pipe_max,
                                           "Mrays_per_s": world * n * W * H / dt_pipe_max / 1e6,
                                           "what": "two frames in flight: frame k+1 traced while frame k is encoded"},
             "jpeg_bytes_per_frame": out["jpeg_bytes"] / n, "raw_bytes_per_frame": W * H * 3,
-            "nvjpeg_device_ms_per_frame": out["encode_ms"] / n, "psnr_db": out["psnr"],
+            "encode_device_ms_per_frame": out["encode_ms"] / n, "psnr_db": out["psnr"],
             "host_opencv_imencode": out["cpu"]}
 
 

@@ -115,6 +115,32 @@ class Action(C.Structure):
     ]
 
 
+HUD_MAX_LINES, HUD_MAX_TEXT = 16, 128
+
+
+class HudLine(C.Structure):
+    """bh8_hud_line: one line of HUD text, cv::putText(FONT_HERSHEY_PLAIN, 1, colour, 1) semantics."""
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("b", C.c_uint8), ("g", C.c_uint8), ("r", C.c_uint8),
+                ("reserved", C.c_uint8), ("text", C.c_char * HUD_MAX_TEXT)]
+
+
+def hud_lines(lines, color=(0, 255, 0)):
+    """[(text, x, y) ...] -> array of HudLine."""
+    arr = (HudLine * max(1, len(lines)))()
+    for k, (text, x, y) in enumerate(lines):
+        arr[k] = HudLine(int(x), int(y), color[0], color[1], color[2], 0, text.encode("latin-1", "replace")[:HUD_MAX_TEXT - 1])
+    return arr
+
+
+def reference_hud(camera, fov_deg=90):
+    """The five lines blackhole_solution_test.cc:309-326 draws, for an abi.Camera (operator<< of cv::Vec3d)."""
+    def vec(v):
+        return "[" + ", ".join("%g" % x for x in v) + "]"
+    return [("Position: " + vec(camera.pos), 0, 10), ("VectorX: " + vec(camera.vx), 0, 25),
+            ("VectorY: " + vec(camera.vy), 0, 40), ("VectorZ: " + vec(camera.vz), 0, 55),
+            ("FoV: %g deg" % fov_deg, 0, 70)]
+
+
 class Basis(C.Structure):
     _fields_ = [("vx", Vec3), ("vy", Vec3), ("vz", Vec3)]
 

@@ -13,6 +13,9 @@
 
 #include <nvjpeg.h>
 
+#include "bh8_hud.h"
+#include "bh8_jpeg.cuh"
+
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -106,6 +109,10 @@ class AviMjpgWriter {
 
   bool is_open() const { return fp_ != nullptr; }
   uint64_t frames() const { return index_.size(); }
+  void abandon() {  // close without finishing (the caller removes the file)
+    if (fp_) std::fclose(fp_);
+    fp_ = nullptr;
+  }
   ~AviMjpgWriter() {
     if (fp_) std::fclose(fp_);
   }
@@ -255,9 +262,74 @@ const char* nvjpeg_status_name(nvjpegStatus_t s) {
 
 }  // namespace
 
+namespace {
+
+// HUD text on the device: the glyph table of bh8_hud_font.h in device memory, one CTA per line, one thread
+// per character (bh8_hud_draw, bh8_hud.h, is the host form of the same blit).
+struct HudDevice {
+  uint16_t* glyph = nullptr;  // [95][16]
+  uint8_t* advance = nullptr; // [95]
+};
+
+__global__ void __launch_bounds__(BH8_HUD_MAX_TEXT) bh8_hud_kernel(uint8_t* bgr, int rows, int cols, const bh8_hud_line* lines,
+                                                                    const uint16_t* glyph, const uint8_t* advance) {
+  const bh8_hud_line& ln = lines[blockIdx.x];
+  const int me = threadIdx.x;
+  int x = ln.x;
+  for (int k = 0; k < me; ++k) {  // pen position of this character; the line ends at its NUL
+    const unsigned char ch = (unsigned char)ln.text[k];
+    if (!ch) return;
+    x += advance[((ch < BH8_HUD_FIRST || ch > BH8_HUD_LAST) ? '?' : ch) - BH8_HUD_FIRST];
+  }
+  const unsigned char ch = (unsigned char)ln.text[me];
+  if (!ch) return;
+  const uint16_t* gl = glyph + (((ch < BH8_HUD_FIRST || ch > BH8_HUD_LAST) ? '?' : ch) - BH8_HUD_FIRST) * BH8_HUD_CELL;
+  for (int gr = 0; gr < BH8_HUD_CELL; ++gr) {
+    const int yy = ln.y + BH8_HUD_TOP + gr;
+    const unsigned bits = gl[gr];
+    if (!bits || yy < 0 || yy >= rows) continue;
+    for (int gx = 0; gx < BH8_HUD_CELL; ++gx) {
+      const int xx = x + gx;
+      if (!((bits >> gx) & 1u) || xx < 0 || xx >= cols) continue;
+      uint8_t* px = bgr + ((size_t)yy * cols + xx) * 3;
+      px[0] = ln.b;
+      px[1] = ln.g;
+      px[2] = ln.r;
+    }
+  }
+}
+
+// The sink's own JPEG encoder (bh8_jpeg.cuh): per frame slot the intermediate buffers and a pinned landing
+// zone for the bitstream.
+struct JpegSlot {
+  int16_t* d_coef = nullptr;
+  uint8_t* d_slots = nullptr;
+  int32_t* d_lens = nullptr;
+  uint32_t* d_offsets = nullptr;
+  uint8_t* d_out = nullptr;    // [0, 8): status (total bytes, overflow flag); the JPEG starts at byte 16
+  uint8_t* h_out = nullptr;    // pinned mirror of d_out
+  bh8_hud_line* d_hud = nullptr;
+  size_t cap = 0;              // bytes of JPEG the output buffers hold
+  size_t copied = 0;           // bytes of JPEG queued for read-back with the frame in flight
+  uint64_t hud_version = 0;    // which bh8_sink_hud() text d_hud holds
+};
+constexpr size_t kJpegOutPrefix = 16;
+
+}  // namespace
+
 struct bh8_sink {
   bh8_ctx* ctx = nullptr;  // nullptr: host-only sink (container fed with ready JPEGs)
   int width = 0, height = 0, quality = 95;
+  // own encoder (default) or nvJPEG ($BH8_SINK_NVJPEG=1, kept for A/B measurements)
+  bool use_nvjpeg = false;
+  bh8jpeg::Geometry geo{};
+  bh8jpeg::Tables* d_tables = nullptr;
+  std::vector<uint8_t> header;
+  JpegSlot jslot[3];       // [0], [1]: bh8_sink_submit's slots; [2]: the synchronous calls
+  size_t copy_hint = 0;    // how much of a frame's output buffer is read back blindly (grows with the frames seen)
+  HudDevice hud_dev;
+  std::vector<bh8_hud_line> hud;  // text drawn into every frame before it is encoded (bh8_sink_hud)
+  uint64_t hud_version = 1;
   AviMjpgWriter avi;
   std::string err;
   std::vector<uint8_t> jpeg;  // bitstream of the last frame
@@ -300,17 +372,116 @@ int sink_fail(bh8_sink* s, int code, const std::string& msg) {
     if (e__ != cudaSuccess) return sink_fail(s, BH8_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
   } while (0)
 
+int jpeg_slot_init(bh8_sink* s, JpegSlot& js) {
+  if (js.d_coef) return BH8_OK;
+  const bh8jpeg::Geometry& g = s->geo;
+  js.cap = static_cast<size_t>(g.n_mcus) * 1024 + 4096;  // raw 4:2:0 data is 384 bytes per MCU
+  BH8_SINK_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&js.d_coef), static_cast<size_t>(g.n_mcus) * 384 * sizeof(int16_t)));
+  BH8_SINK_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&js.d_slots),
+                              static_cast<size_t>(g.n_intervals) * g.ri * bh8jpeg::kSlotBytesPerMcu));
+  BH8_SINK_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&js.d_lens), static_cast<size_t>(g.n_intervals) * sizeof(int32_t)));
+  BH8_SINK_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&js.d_offsets), static_cast<size_t>(g.n_intervals) * sizeof(uint32_t)));
+  BH8_SINK_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&js.d_out), kJpegOutPrefix + js.cap));
+  BH8_SINK_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&js.d_hud), BH8_HUD_MAX_LINES * sizeof(bh8_hud_line)));
+  BH8_SINK_CUDA(s, cudaHostAlloc(reinterpret_cast<void**>(&js.h_out), kJpegOutPrefix + js.cap, cudaHostAllocDefault));
+  BH8_SINK_CUDA(s, cudaMemset(js.d_out, 0, kJpegOutPrefix));
+  BH8_SINK_CUDA(s, cudaMemcpy(js.d_out + kJpegOutPrefix, s->header.data(), s->header.size(), cudaMemcpyHostToDevice));
+  return BH8_OK;
+}
+
+void jpeg_slot_free(JpegSlot& js) {
+  cudaFree(js.d_coef);
+  cudaFree(js.d_slots);
+  cudaFree(js.d_lens);
+  cudaFree(js.d_offsets);
+  cudaFree(js.d_out);
+  cudaFree(js.d_hud);
+  if (js.h_out) cudaFreeHost(js.h_out);
+  js = JpegSlot();
+}
+
+// HUD (if any) and the four encoder kernels for the BGR8 frame at d_bgr, then the read-back of the
+// status words and of the first copy_hint bytes of the stream: all queued on `st`, nothing waits.
+int jpeg_encode_async(bh8_sink* s, JpegSlot& js, void* d_bgr, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+  const bh8jpeg::Geometry& g = s->geo;
+  if (!s->hud.empty()) {
+    if (js.hud_version != s->hud_version) {  // the slot's copy of the text is stale (stream order keeps frames in flight intact)
+      BH8_SINK_CUDA(s, cudaMemcpyAsync(js.d_hud, s->hud.data(), s->hud.size() * sizeof(bh8_hud_line), cudaMemcpyHostToDevice, st));
+      js.hud_version = s->hud_version;
+    }
+    bh8_hud_kernel<<<static_cast<unsigned>(s->hud.size()), BH8_HUD_MAX_TEXT, 0, st>>>(
+        static_cast<uint8_t*>(d_bgr), s->height, s->width, js.d_hud, s->hud_dev.glyph, s->hud_dev.advance);
+  }
+  BH8_SINK_CUDA(s, cudaEventRecord(ev0, st));
+  bh8jpeg::jpeg_transform_kernel<<<g.n_mcus, 64, 0, st>>>(static_cast<const uint8_t*>(d_bgr), s->d_tables, g, js.d_coef);
+  const size_t bit_smem = static_cast<size_t>(bh8jpeg::kEntropyWarps) * g.ri * bh8jpeg::kBitWordsPerMcu * sizeof(uint32_t);
+  bh8jpeg::jpeg_entropy_kernel<<<(g.n_intervals + bh8jpeg::kEntropyWarps - 1) / bh8jpeg::kEntropyWarps,
+                                 bh8jpeg::kEntropyWarps * 32, bit_smem, st>>>(s->d_tables, g, js.d_coef, js.d_slots, js.d_lens,
+                                                                              js.d_offsets, reinterpret_cast<uint32_t*>(js.d_out));
+  bh8jpeg::jpeg_gather_kernel<<<(g.n_intervals * 32 + 255) / 256, 256, 0, st>>>(g, js.d_slots, js.d_lens, js.d_offsets,
+                                                                              js.d_out + kJpegOutPrefix, js.cap);
+  BH8_SINK_CUDA(s, cudaGetLastError());
+  BH8_SINK_CUDA(s, cudaEventRecord(ev1, st));
+  s->ctx->launches += s->hud.empty() ? 3 : 4;
+  js.copied = s->copy_hint < js.cap ? s->copy_hint : js.cap;
+  BH8_SINK_CUDA(s, cudaMemcpyAsync(js.h_out, js.d_out, kJpegOutPrefix + js.copied, cudaMemcpyDeviceToHost, st));
+  return BH8_OK;
+}
+
+// Wait for the frame queued by jpeg_encode_async and leave its bitstream in s->jpeg.
+int jpeg_collect(bh8_sink* s, JpegSlot& js, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+  BH8_SINK_CUDA(s, cudaStreamSynchronize(st));
+  uint32_t status[2];
+  std::memcpy(status, js.h_out, sizeof status);
+  const size_t total = status[0];
+  if (status[1] || total > js.cap || total < s->header.size() + 2)
+    return sink_fail(s, BH8_ECUDA, "JPEG encoder: a restart interval or the frame overflowed its buffer");
+  if (total > js.copied) {  // the blind read-back was too short: fetch the rest, and read more next time
+    BH8_SINK_CUDA(s, cudaMemcpyAsync(js.h_out + kJpegOutPrefix + js.copied, js.d_out + kJpegOutPrefix + js.copied,
+                                     total - js.copied, cudaMemcpyDeviceToHost, st));
+    BH8_SINK_CUDA(s, cudaStreamSynchronize(st));
+  }
+  const size_t want = total + total / 4 + 65536;
+  if (want > s->copy_hint) s->copy_hint = want;
+  s->jpeg.assign(js.h_out + kJpegOutPrefix, js.h_out + kJpegOutPrefix + total);
+  float ms = 0;
+  BH8_SINK_CUDA(s, cudaEventElapsedTime(&ms, ev0, ev1));
+  s->encode_ms += ms;
+  return BH8_OK;
+}
+
 int sink_gpu_init(bh8_sink* s) {
   Device& d = s->ctx->dev[0];
   BH8_SINK_CUDA(s, cudaSetDevice(d.ordinal));
+  BH8_SINK_CUDA(s, cudaEventCreate(&s->ev0));
+  BH8_SINK_CUDA(s, cudaEventCreate(&s->ev1));
+  {  // HUD glyphs
+    BH8_SINK_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&s->hud_dev.glyph), sizeof bh8_hud_glyph));
+    BH8_SINK_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&s->hud_dev.advance), sizeof bh8_hud_advance));
+    BH8_SINK_CUDA(s, cudaMemcpy(s->hud_dev.glyph, bh8_hud_glyph, sizeof bh8_hud_glyph, cudaMemcpyHostToDevice));
+    BH8_SINK_CUDA(s, cudaMemcpy(s->hud_dev.advance, bh8_hud_advance, sizeof bh8_hud_advance, cudaMemcpyHostToDevice));
+  }
+  if (const char* e = std::getenv("BH8_SINK_NVJPEG")) s->use_nvjpeg = std::atoi(e) != 0;
+  if (!s->use_nvjpeg) {
+    int ri = 2;  // restart interval in MCUs: see bh8_jpeg.cuh
+    if (const char* e = std::getenv("BH8_SINK_RESTART_INTERVAL")) ri = std::atoi(e);
+    if (ri < 1 || ri > 16) return sink_fail(s, BH8_EINVAL, "BH8_SINK_RESTART_INTERVAL must be in 1..16 (MCUs)");
+    s->header.resize(1024);
+    s->header.resize(static_cast<size_t>(bh8jpeg::make_header(s->width, s->height, s->quality, ri, s->header.data())));
+    s->geo = bh8jpeg::make_geometry(s->width, s->height, ri, static_cast<int>(s->header.size()));
+    bh8jpeg::Tables t;
+    bh8jpeg::make_tables(s->quality, &t);
+    BH8_SINK_CUDA(s, cudaMalloc(reinterpret_cast<void**>(&s->d_tables), sizeof t));
+    BH8_SINK_CUDA(s, cudaMemcpy(s->d_tables, &t, sizeof t, cudaMemcpyHostToDevice));
+    s->copy_hint = 1 << 20;
+    return BH8_OK;
+  }
   BH8_NVJPEG(s, nvjpegCreateSimple(&s->handle));
   BH8_NVJPEG(s, nvjpegEncoderStateCreate(s->handle, &s->state, d.stream));
   BH8_NVJPEG(s, nvjpegEncoderParamsCreate(s->handle, &s->params, d.stream));
   BH8_NVJPEG(s, nvjpegEncoderParamsSetQuality(s->params, s->quality, d.stream));
   BH8_NVJPEG(s, nvjpegEncoderParamsSetSamplingFactors(s->params, NVJPEG_CSS_420, d.stream));
   BH8_NVJPEG(s, nvjpegEncoderParamsSetOptimizedHuffman(s->params, 0, d.stream));
-  BH8_SINK_CUDA(s, cudaEventCreate(&s->ev0));
-  BH8_SINK_CUDA(s, cudaEventCreate(&s->ev1));
   return BH8_OK;
 }
 
@@ -319,6 +490,12 @@ int sink_gpu_init(bh8_sink* s) {
 int sink_encode(bh8_sink* s, const void* d_bgr) {
   Device& d = s->ctx->dev[0];
   BH8_SINK_CUDA(s, cudaSetDevice(d.ordinal));
+  if (!s->use_nvjpeg) {
+    JpegSlot& js = s->jslot[2];
+    int rc = jpeg_slot_init(s, js);
+    if (rc == BH8_OK) rc = jpeg_encode_async(s, js, const_cast<void*>(d_bgr), d.stream, s->ev0, s->ev1);
+    return rc != BH8_OK ? rc : jpeg_collect(s, js, d.stream, s->ev0, s->ev1);
+  }
   nvjpegImage_t img{};
   img.channel[0] = static_cast<unsigned char*>(const_cast<void*>(d_bgr));
   img.pitch[0] = static_cast<size_t>(s->width) * 3;
@@ -339,17 +516,56 @@ int sink_encode(bh8_sink* s, const void* d_bgr) {
 }
 
 int sink_commit(bh8_sink* s) {
-  s->frames++;
-  s->jpeg_bytes += s->jpeg.size();
   if (s->avi.is_open() && !s->avi.append(s->jpeg.data(), s->jpeg.size(), &s->err)) return BH8_EINVAL;
+  s->frames++;  // only frames that reached the file (or the caller, for a sink without one) are counted
+  s->jpeg_bytes += s->jpeg.size();
   return BH8_OK;
+}
+
+// Everything sink_gpu_init / the first frames created on the device (bh8_sink_close, and bh8_sink_open's
+// failure path).
+void sink_gpu_teardown(bh8_sink* s) {
+  if (!s->ctx) return;
+  cudaSetDevice(s->ctx->dev[0].ordinal);
+  cudaStreamSynchronize(s->ctx->dev[0].stream);
+  for (bh8_sink::Slot& sl : s->slot) {
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
+    if (sl.state) nvjpegEncoderStateDestroy(sl.state);
+    if (sl.d_frame) cudaFree(sl.d_frame);
+    if (sl.ev0) cudaEventDestroy(sl.ev0);
+    if (sl.ev1) cudaEventDestroy(sl.ev1);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+    sl = bh8_sink::Slot();
+  }
+  for (JpegSlot& js : s->jslot) jpeg_slot_free(js);
+  cudaFree(s->d_tables);
+  cudaFree(s->hud_dev.glyph);
+  cudaFree(s->hud_dev.advance);
+  if (s->params) nvjpegEncoderParamsDestroy(s->params);
+  if (s->state) nvjpegEncoderStateDestroy(s->state);
+  if (s->handle) nvjpegDestroy(s->handle);
+  if (s->d_frame) cudaFree(s->d_frame);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  s->d_tables = nullptr;
+  s->hud_dev = HudDevice();
+  s->params = nullptr;
+  s->state = nullptr;
+  s->handle = nullptr;
+  s->d_frame = nullptr;
+  s->ev0 = s->ev1 = nullptr;
 }
 
 // Fetch the bitstream of the frame in flight on this slot and append it to the file.
 int sink_drain(bh8_sink* s, bh8_sink::Slot& sl) {
   if (!sl.busy) return BH8_OK;
-  sl.busy = false;
   BH8_SINK_CUDA(s, cudaSetDevice(s->ctx->dev[0].ordinal));
+  if (!s->use_nvjpeg) {
+    const int rc = jpeg_collect(s, s->jslot[&sl - s->slot], sl.stream, sl.ev0, sl.ev1);
+    sl.busy = false;
+    return rc != BH8_OK ? rc : sink_commit(s);
+  }
+  sl.busy = false;
   size_t length = 0;
   BH8_NVJPEG(s, nvjpegEncodeRetrieveBitstream(s->handle, sl.state, nullptr, &length, sl.stream));
   s->jpeg.resize(length);
@@ -396,11 +612,60 @@ int bh8_sink_open(bh8_ctx* ctx, const char* avi_path, int width, int height, dou
     const int rc = sink_gpu_init(s);
     if (rc != BH8_OK) {
       fail(ctx, rc, "bh8_sink_open: " + s->err);
+      sink_gpu_teardown(s);
+      s->avi.abandon();  // no half-written file is left behind
+      if (avi_path) std::remove(avi_path);
       delete s;
       return rc;
     }
   }
   *out = s;
+  return BH8_OK;
+}
+
+int bh8_sink_hud(bh8_sink* s, const bh8_hud_line* lines, int n_lines) {
+  if (!s || n_lines < 0 || n_lines > BH8_HUD_MAX_LINES || (n_lines > 0 && !lines)) return BH8_EINVAL;
+  if (!s->ctx) return sink_fail(s, BH8_EINVAL, "this sink was opened without a context");
+  if (s->use_nvjpeg && n_lines > 0) return sink_fail(s, BH8_EUNSUPPORTED, "the HUD needs the sink's own encoder");
+  // frames in flight may still be copying the old text out of s->hud (pageable memory is staged at the call,
+  // so they are not, but a drained pipeline keeps this obviously right)
+  const int rcf = sink_flush(s);
+  if (rcf != BH8_OK) return rcf;
+  s->hud.assign(lines, lines + n_lines);
+  for (bh8_hud_line& ln : s->hud) ln.text[BH8_HUD_MAX_TEXT - 1] = 0;
+  s->hud_version++;
+  return BH8_OK;
+}
+
+int bh8_hud_draw_device(bh8_ctx* ctx, void* d_bgr_frame, int width, int height, const bh8_hud_line* lines, int n_lines) {
+  if (!ctx) return BH8_EINVAL;
+  if (!d_bgr_frame || width < 1 || height < 1 || n_lines < 1 || n_lines > BH8_HUD_MAX_LINES || !lines)
+    return fail(ctx, BH8_EINVAL, "bad arguments to bh8_hud_draw_device");
+  Device& d = ctx->dev[0];
+  BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+  uint16_t* glyph = nullptr;
+  uint8_t* advance = nullptr;
+  bh8_hud_line* d_lines = nullptr;
+  std::vector<bh8_hud_line> copy(lines, lines + n_lines);
+  for (bh8_hud_line& ln : copy) ln.text[BH8_HUD_MAX_TEXT - 1] = 0;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&glyph), sizeof bh8_hud_glyph);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&advance), sizeof bh8_hud_advance);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d_lines), copy.size() * sizeof(bh8_hud_line));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(glyph, bh8_hud_glyph, sizeof bh8_hud_glyph, cudaMemcpyHostToDevice, d.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(advance, bh8_hud_advance, sizeof bh8_hud_advance, cudaMemcpyHostToDevice, d.stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d_lines, copy.data(), copy.size() * sizeof(bh8_hud_line), cudaMemcpyHostToDevice, d.stream);
+  if (e == cudaSuccess) {
+    bh8_hud_kernel<<<static_cast<unsigned>(n_lines), BH8_HUD_MAX_TEXT, 0, d.stream>>>(static_cast<uint8_t*>(d_bgr_frame), height,
+                                                                                     width, d_lines, glyph, advance);
+    e = cudaGetLastError();
+    ctx->launches++;
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+  cudaFree(glyph);
+  cudaFree(advance);
+  cudaFree(d_lines);
+  if (e != cudaSuccess) return fail(ctx, BH8_ECUDA, std::string("bh8_hud_draw_device: ") + cudaGetErrorString(e));
   return BH8_OK;
 }
 
@@ -448,7 +713,7 @@ int bh8_sink_submit(bh8_sink* s, const bh8_scene* scene, const bh8_camera* cam, 
     BH8_SINK_CUDA(s, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
     BH8_SINK_CUDA(s, cudaEventCreate(&sl.ev0));
     BH8_SINK_CUDA(s, cudaEventCreate(&sl.ev1));
-    BH8_NVJPEG(s, nvjpegEncoderStateCreate(s->handle, &sl.state, sl.stream));
+    if (s->use_nvjpeg) BH8_NVJPEG(s, nvjpegEncoderStateCreate(s->handle, &sl.state, sl.stream));
     BH8_SINK_CUDA(s, cudaMalloc(&sl.d_frame, static_cast<size_t>(s->width) * s->height * 3));
   }
   bh8_params prm{};
@@ -456,6 +721,15 @@ int bh8_sink_submit(bh8_sink* s, const bh8_scene* scene, const bh8_camera* cam, 
   prm.pixel_format = BH8_PIXEL_BGR8;
   const int rc = launch_frame(s->ctx, d, scene, cam, &prm, sl.d_frame, nullptr, nullptr, nullptr, sl.stream);
   if (rc != BH8_OK) return sink_fail(s, rc, s->ctx->err);
+  if (!s->use_nvjpeg) {
+    JpegSlot& js = s->jslot[s->submitted & 1];
+    int rcj = jpeg_slot_init(s, js);
+    if (rcj == BH8_OK) rcj = jpeg_encode_async(s, js, sl.d_frame, sl.stream, sl.ev0, sl.ev1);
+    if (rcj != BH8_OK) return rcj;
+    sl.busy = true;
+    s->submitted++;
+    return BH8_OK;
+  }
   nvjpegImage_t img{};
   img.channel[0] = static_cast<unsigned char*>(sl.d_frame);
   img.pitch[0] = static_cast<size_t>(s->width) * 3;
@@ -537,23 +811,7 @@ int bh8_sink_close(bh8_sink* s, uint64_t* file_bytes) {
   if (file_bytes) *file_bytes = 0;
   int rc = sink_flush(s);  // frames still in flight belong to the file
   if (s->avi.is_open() && !s->avi.close(file_bytes, &s->err)) rc = BH8_EINVAL;
-  if (s->ctx) {
-    cudaSetDevice(s->ctx->dev[0].ordinal);
-    for (bh8_sink::Slot& sl : s->slot) {
-      if (sl.stream) cudaStreamSynchronize(sl.stream);
-      if (sl.state) nvjpegEncoderStateDestroy(sl.state);
-      if (sl.d_frame) cudaFree(sl.d_frame);
-      if (sl.ev0) cudaEventDestroy(sl.ev0);
-      if (sl.ev1) cudaEventDestroy(sl.ev1);
-      if (sl.stream) cudaStreamDestroy(sl.stream);
-    }
-    if (s->params) nvjpegEncoderParamsDestroy(s->params);
-    if (s->state) nvjpegEncoderStateDestroy(s->state);
-    if (s->handle) nvjpegDestroy(s->handle);
-    if (s->d_frame) cudaFree(s->d_frame);
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
-  }
+  sink_gpu_teardown(s);
   delete s;
   return rc;
 }

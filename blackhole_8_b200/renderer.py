@@ -82,6 +82,8 @@ def load_library(path=None):
         "bh8_sink_render": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params)]),
         "bh8_sink_submit": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Camera), C.POINTER(abi.Params)]),
         "bh8_sink_flush": (i32, [vp]),
+        "bh8_sink_hud": (i32, [vp, C.POINTER(abi.HudLine), i32]),
+        "bh8_hud_draw_device": (i32, [vp, vp, i32, i32, C.POINTER(abi.HudLine), i32]),
         "bh8_sink_merge": (i32, [C.POINTER(C.c_char_p), i32, C.c_char_p, C.POINTER(u64), C.POINTER(u64)]),
         "bh8_sink_write_device": (i32, [vp, vp]),
         "bh8_sink_append_jpeg": (i32, [vp, vp, C.c_size_t]),
@@ -230,6 +232,11 @@ class Renderer:
         self._check(self.lib.bh8_render_device(self._ctx, C.byref(snap.scene), C.byref(snap.camera), C.byref(prm),
                                                C.c_void_p(d_pixels), C.c_void_p(d_cls), C.c_void_p(d_key),
                                                C.c_void_p(d_steps)))
+
+    def hud_draw_device(self, d_bgr_frame, width, height, lines, color=(0, 255, 0)):
+        """cv::putText semantics on a BGR8 frame in device memory (bh8_hud_draw_device)."""
+        arr = abi.hud_lines(lines, color)
+        self._check(self.lib.bh8_hud_draw_device(self._ctx, C.c_void_p(d_bgr_frame), width, height, arr, len(lines)))
 
     def sync(self):
         self._check(self.lib.bh8_sync(self._ctx))
@@ -383,6 +390,12 @@ class VideoSink:
 
     def flush(self):
         self._check(self.lib.bh8_sink_flush(self._h))
+
+    def hud(self, lines, color=(0, 255, 0)):
+        """Text drawn on the device into every frame rendered from now on, before it is encoded: the
+        reference's cv::putText block (blackhole_solution_test.cc:309-326).  lines: [(text, x, y), ...]; [] = off."""
+        arr = abi.hud_lines(lines, color)
+        self._check(self.lib.bh8_sink_hud(self._h, arr, len(lines)))
 
     def write_device(self, d_bgr_frame):
         self._check(self.lib.bh8_sink_write_device(self._h, C.c_void_p(d_bgr_frame)))

@@ -235,8 +235,10 @@ int bh8_measure_stepping(bh8_ctx* ctx, int fp32, double* updates_per_s);
 /* ---- Frame sink ------------------------------------------------------------
  * Replaces cv::VideoWriter(path, cv::VideoWriter::fourcc('M','J','P','G'), fps, size, true) and
  * out_capture.write(frame) of blackhole_solution_test.cc:71-72,334: a Motion-JPEG AVI file whose
- * frames are JPEG-encoded ON THE GPU (nvJPEG, 4:2:0, baseline Huffman) straight from the
- * device-resident BGR8 frame, so only the bitstream crosses PCIe.
+ * frames are JPEG-encoded ON THE GPU by this library's own kernels (baseline, 4:2:0, IJG quantisation
+ * tables scaled by `quality`, standard Huffman tables, restart markers; csrc/bh8_jpeg.cuh) straight from
+ * the device-resident BGR8 frame, so only the bitstream crosses PCIe.  $BH8_SINK_NVJPEG=1 selects
+ * nvJPEG instead (kept for comparison).
  *   ctx != NULL: GPU sink on device 0 of the context.  ctx == NULL: host-only container that is fed
  *                ready JPEGs with bh8_sink_append_jpeg() (no GPU needed).
  *   avi_path:    file to write, or NULL to encode only (read each frame with bh8_sink_last_jpeg()).
@@ -254,6 +256,20 @@ int bh8_sink_render(bh8_sink* sink, const bh8_scene* scene, const bh8_camera* ca
  * bh8_sink_stats() describe the frames appended so far. */
 int bh8_sink_submit(bh8_sink* sink, const bh8_scene* scene, const bh8_camera* cam, const bh8_params* params);
 int bh8_sink_flush(bh8_sink* sink);
+/* HUD text of the reference's frames: blackhole_solution_test.cc:309-326 draws five lines of
+ * cv::putText(FONT_HERSHEY_PLAIN, 1, green, 1) into the frame BEFORE out_capture.write (:334).  The lines set
+ * here are drawn on the device into every frame the sink renders from now on, before it is encoded
+ * (n_lines = 0: none); for text inside the image the pixels equal cv::putText's bit for bit. */
+#define BH8_HUD_MAX_LINES 16
+#define BH8_HUD_MAX_TEXT 128
+typedef struct bh8_hud_line {
+  int32_t x, y;       /* bottom-left corner of the text, as in cv::putText */
+  uint8_t b, g, r, reserved;
+  char text[BH8_HUD_MAX_TEXT]; /* NUL-terminated */
+} bh8_hud_line;
+int bh8_sink_hud(bh8_sink* sink, const bh8_hud_line* lines, int n_lines);
+/* The same blit on any BGR8 frame in device memory (device 0 of the context); synchronous. */
+int bh8_hud_draw_device(bh8_ctx* ctx, void* d_bgr_frame, int width, int height, const bh8_hud_line* lines, int n_lines);
 /* Encode and append a BGR8 frame that is already in device memory (H * W * 3 bytes, device 0). */
 int bh8_sink_write_device(bh8_sink* sink, const void* d_bgr_frame);
 int bh8_sink_append_jpeg(bh8_sink* sink, const uint8_t* jpeg, size_t bytes);
