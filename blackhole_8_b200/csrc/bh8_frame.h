@@ -166,9 +166,18 @@ BH8F_HD int bh8_build_frame_core(const bh8_scene* scene, const bh8_camera* cam, 
   if (cam->width < 1 || cam->height < 1 || cam->width > 65536 || cam->height > 65536) return BH8F_CAMERA_SIZE;
   if (!linear && (prm->nstep < 2 || prm->nstep > 32767)) return BH8F_NSTEP;
   if (prm->pixel_format < 0 || prm->pixel_format > BH8_PIXEL_BGR8) return BH8F_PIXEL_FORMAT;
-  // no hole (linear tracer): a unit-mass stand-in at the origin feeds the (unused) geodesic constants
+  // The linear tracer bends nothing: bh_index may be -1.  A StaticBlackhole among the objects is then just
+  // a black sphere of radius 2M to FindCollision (one such sphere: the kernels hold one radius); with no
+  // hole at all a unit-mass stand-in at the origin feeds the (unused) geodesic constants.
   const double no_hole_pos[3] = {0.0, 0.0, 0.0};
-  const bh8_object* bho = scene->bh_index >= 0 ? &scene->obj[scene->bh_index] : nullptr;
+  int hole = scene->bh_index;
+  if (linear && hole < 0)
+    for (int k = 0; k < scene->n_obj; ++k)
+      if (scene->obj[k].kind == BH8_KIND_BLACKHOLE) {
+        if (hole >= 0) return BH8F_TWO_HOLES;
+        hole = k;
+      }
+  const bh8_object* bho = hole >= 0 ? &scene->obj[hole] : nullptr;
   const double bh_mass = bho ? bho->mass : 1.0;
   const double* bh_pos = bho ? bho->v[0] : no_hole_pos;
   if (!(bh_mass > 0)) return BH8F_MASS;
@@ -241,7 +250,7 @@ BH8F_HD int bh8_build_frame_core(const bh8_scene* scene, const bh8_camera* cam, 
       case BH8_KIND_BLACKHOLE:
         q->cls = BH8_CLASS_HORIZON;
         f->hole_mask |= 1u << k;
-        if (k != scene->bh_index) return BH8F_TWO_HOLES;
+        if (k != hole) return BH8F_TWO_HOLES;
         for (int i = 0; i < 3; ++i) q->p0[i] = o->v[0][i];
         continue;
       case BH8_KIND_ANNULUS:

@@ -41,8 +41,7 @@ class Renderer {
     const SceneSnapshot snap = Snapshot(manager, blackhole);
     const bh8_camera cam = Snapshot(camera);
     UploadTextures(snap);
-    if (frame->empty() || frame->rows != cam.height || frame->cols != cam.width || frame->type() != CV_8UC3)
-      *frame = cv::Mat(cam.height, cam.width, CV_8UC3);
+    EnsureFrame(cam, frame);
     const bh8_scene scene = snap.view();
     bh8_params prm{};
     prm.nstep = nstep;
@@ -58,8 +57,7 @@ class Renderer {
     const SceneSnapshot snap = SnapshotFlat(manager);
     const bh8_camera cam = Snapshot(camera);
     UploadTextures(snap);
-    if (frame->empty() || frame->rows != cam.height || frame->cols != cam.width || frame->type() != CV_8UC3)
-      *frame = cv::Mat(cam.height, cam.width, CV_8UC3);
+    EnsureFrame(cam, frame);
     const bh8_scene scene = snap.view();
     bh8_params prm{};
     prm.tracer = BH8_TRACER_LINEAR;
@@ -76,8 +74,10 @@ class Renderer {
     const int n = static_cast<int>(scenes.size());
     const size_t bytes = static_cast<size_t>(cameras[0].width) * cameras[0].height * 3;
     std::vector<bh8_scene> views(n);
-    for (int i = 0; i < n; ++i) views[i] = scenes[i].view();
-    UploadTextures(scenes[0]);
+    for (int i = 0; i < n; ++i) {
+      views[i] = scenes[i].view();
+      UploadTextures(scenes[i]);  // every scene's textures (normally the same buffers: sent once)
+    }
     std::vector<unsigned char> pixels(bytes * n);
     bh8_params prm{};
     prm.nstep = nstep;
@@ -96,20 +96,40 @@ class Renderer {
     if (rc != BH8_OK) throw std::runtime_error(std::string("bh8: ") + bh8_last_error(ctx_));
   }
 
-  // Textures are re-sent only when a slot's pixel buffer changes.
+  // The frame the kernels' rows are copied into: H x W CV_8UC3 with rows back to back (a ROI or padded Mat is
+  // replaced by a fresh one rather than written through with the wrong stride).
+  static void EnsureFrame(const bh8_camera& cam, cv::Mat* frame) {
+    if (frame->empty() || frame->rows != cam.height || frame->cols != cam.width || frame->type() != CV_8UC3 ||
+        !frame->isContinuous())
+      *frame = cv::Mat(cam.height, cam.width, CV_8UC3);
+  }
+
+  // Textures are re-sent when a slot's image changes: another buffer, another size or row stride.  (A caller
+  // that rewrites the pixels of the SAME buffer in place calls InvalidateTextures().)
+  struct TexKey {
+    const unsigned char* data = nullptr;
+    int rows = 0, cols = 0;
+    size_t step = 0;
+    bool operator==(const TexKey& o) const { return data == o.data && rows == o.rows && cols == o.cols && step == o.step; }
+  };
   void UploadTextures(const SceneSnapshot& snap) {
-    if (uploaded_.size() < snap.textures.size()) uploaded_.resize(snap.textures.size(), nullptr);
+    if (uploaded_.size() < snap.textures.size()) uploaded_.resize(snap.textures.size());
     for (size_t t = 0; t < snap.textures.size(); ++t) {
       const cv::Mat& m = snap.textures[t];
-      if (uploaded_[t] == m.data) continue;
-      Check(bh8_set_texture(ctx_, static_cast<int>(t), m.data, m.rows, m.cols, static_cast<size_t>(m.cols) * 3));
-      uploaded_[t] = m.data;
+      const TexKey key{m.data, m.rows, m.cols, static_cast<size_t>(m.step)};
+      if (uploaded_[t] == key) continue;
+      Check(bh8_set_texture(ctx_, static_cast<int>(t), m.data, m.rows, m.cols, static_cast<size_t>(m.step)));
+      uploaded_[t] = key;
     }
   }
 
+ public:
+  void InvalidateTextures() { uploaded_.clear(); }
+
+ private:
   bh8_ctx* ctx_ = nullptr;
   bh8_stats stats_{};
-  std::vector<const unsigned char*> uploaded_;
+  std::vector<TexKey> uploaded_;
   friend class VideoWriter;
   friend class Script;
 };

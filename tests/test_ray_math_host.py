@@ -207,3 +207,27 @@ def test_frozen_lanes_are_inert(name):
         L.bh8_harness_set_frozen_updates(0)
     for k in ("bgr", "cls", "key", "steps"):
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_flat_space_scene_may_contain_a_hole_as_a_black_sphere():
+    """ray_tracer_test.cc's scene with a StaticBlackhole dropped in: FindCollision treats it as a sphere of
+    radius 2M (blackhole_solution.h:65-88), the linear tracer bends nothing, so bh_index stays -1.  The frame
+    builder used to reject the scene ('more than one black hole')."""
+    g = O.load_golden("cfg10_flat_800x450")
+    d = g["snap"].to_dict()
+    d["width"], d["height"] = 200, 112
+    d["camera"].update(width=200, height=112, focus_len=d["camera"]["focus_len"] * 200 / 800)
+    hole = dict(d["objects"][0], kind=abi.KIND_BLACKHOLE, key=9, tex_id=-1, pattern=0, mass=30.0,
+                v=[-150.0, 60.0, 60.0] + [0.0] * 12)
+    d["objects"] = [hole] + d["objects"]
+    assert d["bh_index"] == -1
+    snap = abi.SceneSnapshot.from_dict(d)
+    got = harness_render(snap)
+    ref = O.render(snap)
+    assert (ref["cls"] == abi.CLASS_HORIZON).sum() > 50  # the sphere is in view
+    for k in ("bgr", "cls", "key", "steps"):
+        assert np.array_equal(got[k], ref[k]), k
+    # two spheres: the kernels hold one radius, so this must be refused, with the right message
+    d["objects"] = [dict(hole, key=10, v=[0.0, 300.0, 0.0] + [0.0] * 12)] + d["objects"]
+    with pytest.raises(AssertionError, match="more than one black hole"):
+        harness_render(abi.SceneSnapshot.from_dict(d))
