@@ -888,7 +888,8 @@ def main():
         w_launch = st.warps / world
         passes = st.resolve_passes / world
         slots = st.update_slots / world
-        fixed_flops = 32.0 * (m["fp64_flops_fixed_per_lane"] * w_launch + m["fp64_flops_per_pass_per_lane"] * passes)
+        fixed_flops = 32.0 * m.get("fp64_lane_fraction", 1.0) * (m["fp64_flops_fixed_per_lane"] * w_launch +
+                                                                 m["fp64_flops_per_pass_per_lane"] * passes)
         instr_per_warp = (m["instr_fixed"] * w_launch + m["instr_per_update_slot"] * slots +
                           m["instr_per_pass"] * passes) / w_launch
     executed = stepping_flops + (fixed_flops or 0.0)
