@@ -173,24 +173,21 @@ __device__ __forceinline__ void trace_patch(const Bh8Frame& f, const DeviceFetch
     lane_setup(f, x, y, L, mail);
     lane_park_constants(L, mail);
   }
-  for (bool done = false; !done;) {
+  for (;;) {
     // Lean stepping: the same straight-line update for every lane (frozen lanes are inert, see
     // lane_freeze), a few updates per round of warp votes, until the warp decides to attend to its
     // parked lanes (or every ray has ended).  `waited` and the update's constants live in this phase
     // only: nothing of the warp's bookkeeping is carried across the exact pass.
-    int waited = 0;
+    int waited = 0, todo;
     const StepConst sc = StepConst::load_shared(sc_addr);
-    for (;;) {
+    do {
 #pragma unroll
       for (int k = 0; k < UPV; ++k) lane_update(f, L, mail, sc);
       if (STATS) ++sc_n.n_iter;
       const unsigned present = __reduce_or_sync(0xffffffffu, (unsigned)L.state);
-      const int todo = warp_decide(present, waited, f.resolve_wait);
-      if (todo == kWarpStep) continue;
-      done = (todo == kWarpDone);  // every ray of the patch has ended
-      break;
-    }
-    if (done) break;
+      todo = warp_decide(present, waited, f.resolve_wait);
+    } while (todo == kWarpStep);
+    if (todo == kWarpDone) break;  // every ray of the patch has ended
     if (STATS) {
       ++sc_n.n_pass;
       if (L.state & (kPend | kPendChord)) ++sc_n.n_test;
@@ -258,6 +255,10 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
 
   uint32_t sc_addr;
   const Mail mail = make_mail(f, tid, lane, warp, &sc_addr);
+#if defined(BH8_DUMMY_SMEM)  // occupancy experiment: shared memory nobody uses, to run 4 instead of 5 CTAs per SM
+  __shared__ volatile char sh_dummy[BH8_DUMMY_SMEM];
+  if (f.width < 0) sh_dummy[tid] = 1;
+#endif
   const DeviceFetch fetch{tex};
   SchedCount n;
   trace_patch<NN, STATS, UPV>(f, fetch, mail, sc_addr, x, y, inside, n);

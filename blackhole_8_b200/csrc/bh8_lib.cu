@@ -64,6 +64,7 @@ struct bh8_ctx {
   uint64_t next_ticket = 0;  // bh8_submit
   bool submit_slot_streams = true;  // $BH8_SUBMIT_ONE_STREAM=1: kernels on one stream, copies on another (A/B knob)
   int resolve_wait = 0x7fffffff;    // $BH8_RESOLVE_WAIT: tuning knob for the batching window, read once at creation
+  size_t extra_smem = 0;            // $BH8_EXTRA_SMEM: unused dynamic shared memory per CTA (occupancy experiments)
   std::vector<void*> owned;  // bh8_frame_alloc results (device 0)
 };
 
@@ -157,9 +158,9 @@ int launch_built(bh8_ctx* ctx, Device& d, Bh8Frame& f, void* d_pixels, void* d_c
 #define BH8_LAUNCH2(NN_, ST_)                                                              \
   do {                                                                                     \
     if (f.nstep >= bh8::kFineNstep)                                                        \
-      bh8::bh8_render_kernel<NN_, ST_, 3><<<grid, bh8::kThreads, 0, st>>>(f, tex, out);    \
+      bh8::bh8_render_kernel<NN_, ST_, 3><<<grid, bh8::kThreads, ctx->extra_smem, st>>>(f, tex, out);    \
     else                                                                                   \
-      bh8::bh8_render_kernel<NN_, ST_, 2><<<grid, bh8::kThreads, 0, st>>>(f, tex, out);    \
+      bh8::bh8_render_kernel<NN_, ST_, 2><<<grid, bh8::kThreads, ctx->extra_smem, st>>>(f, tex, out);    \
   } while (0)
 #define BH8_LAUNCH(NN_)                                                                    \
   do {                                                                                     \
@@ -270,6 +271,7 @@ int bh8_create(bh8_ctx** out, const int* devices, int n_dev) {
   ctx->n_dev = n_dev;
   if (const char* one = std::getenv("BH8_SUBMIT_ONE_STREAM")) ctx->submit_slot_streams = std::atoi(one) == 0;
   if (const char* w = std::getenv("BH8_RESOLVE_WAIT")) ctx->resolve_wait = std::atoi(w);
+  if (const char* x = std::getenv("BH8_EXTRA_SMEM")) ctx->extra_smem = static_cast<size_t>(std::atoi(x));
   for (int i = 0; i < n_dev; ++i) {
     Device& d = ctx->dev[i];
     d.ordinal = devices ? devices[i] : i;
