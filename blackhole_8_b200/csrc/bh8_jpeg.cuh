@@ -17,9 +17,9 @@
 //                           zigzag order, int16
 //   jpeg_entropy_kernel     one warp per restart interval, lanes share a block's coefficients: -> bytes in the
 //                           interval's slot
-//                           interval's slot; the CTA that finishes last scans the slot lengths (+ markers,
-//                           + header) -> offsets, total
-//   jpeg_gather_kernel      one warp per interval: slot -> its place in the stream, RSTm / EOI marker
+//                           interval's slot; per-CTA byte totals
+//   jpeg_gather_kernel      one warp per interval: the CTA sums the totals of the CTAs before it (its place in
+//                           the stream), then slot -> stream, RSTm / EOI marker
 //
 // The per-MCU arithmetic and the bit writer are __host__ __device__: tests/host_harness runs the very same
 // code on the CPU and OpenCV decodes the result (tests/test_jpeg_host.py); the shipped library only calls
@@ -313,7 +313,8 @@ BH8J_HD int encode_interval(const Tables& t, const int16_t* coef, int first, int
 // One 16x16 MCU per 64-thread CTA: BGR8 pixels (edge replication beyond the frame) -> YCbCr, chroma 2x2 box
 // average, level shift, row DCTs, column DCTs, quantisation, zigzag order.
 __global__ void __launch_bounds__(64) jpeg_transform_kernel(const uint8_t* __restrict__ bgr, const Tables* __restrict__ tp,
-                                                            Geometry g, int16_t* __restrict__ coef) {
+                                                            Geometry g, int16_t* __restrict__ coef, uint32_t* status) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) status[1] = 0u;  // the frame's overflow flag (set by the entropy kernel)
   __shared__ float sy[256], scb[256], scr[256];  // full-resolution planes of the MCU
   __shared__ float blk[6][64];                   // the six blocks, then their row transforms (in place per row)
   __shared__ __align__(16) uint32_t raw[192];    // the MCU's 16 rows of 48 bytes; later its 384 coefficients (int16)
@@ -407,7 +408,7 @@ __device__ __forceinline__ void put_bits(uint32_t* words, uint32_t off, uint64_t
 __global__ void __launch_bounds__(kEntropyWarps * 32) jpeg_entropy_kernel(const Tables* __restrict__ tp, Geometry g,
                                                                          const int16_t* __restrict__ coef,
                                                                          uint8_t* __restrict__ slots, int32_t* lens,
-                                                                         uint32_t* offsets, uint32_t* status) {
+                                                                         uint32_t* cta_bytes, uint32_t* status) {
   extern __shared__ uint32_t sh_bits[];  // kEntropyWarps x (ri * kBitWordsPerMcu) words
   __shared__ uint32_t sh_dc[2][12], sh_ac[2][256];  // the Huffman tables: looked up with data-dependent indices
   for (int k = threadIdx.x; k < 2 * 256; k += blockDim.x) (&sh_ac[0][0])[k] = (&tp->ac_code[0][0])[k];
@@ -423,18 +424,34 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) jpeg_entropy_kernel(const 
   const int first = i * g.ri, count = min(g.ri, g.n_mcus - first);
   uint32_t total = 0;  // bits so far (warp-uniform)
   int pred0 = 0, pred1 = 0, pred2 = 0;  // DC predictors (lane 0's are the ones used)
-  // the coefficients of the NEXT block are fetched while this one is coded
+  // All 384 coefficients of the NEXT MCU are fetched (twelve independent loads per lane) while this one is
+  // coded from registers: one trip to L2 per MCU is exposed at most, instead of one per block.
   const int16_t* zz0 = coef + (size_t)first * 384;
-  const int n_blocks = count * 6;
-  int nc0 = zz0[lane], nc1 = zz0[lane + 32];
-  for (int m = first, blk_i = 0; m < first + count; ++m) {
-    for (int b = 0; b < 6; ++b, ++blk_i) {
-      const int which = b < 4 ? 0 : 1;
-      const int c0 = nc0, c1 = nc1;
-      if (blk_i + 1 < n_blocks) {
-        nc0 = zz0[(blk_i + 1) * 64 + lane];
-        nc1 = zz0[(blk_i + 1) * 64 + lane + 32];
+  int16_t nx0[6], nx1[6];
+#pragma unroll
+  for (int b = 0; b < 6; ++b) {
+    nx0[b] = zz0[b * 64 + lane];
+    nx1[b] = zz0[b * 64 + lane + 32];
+  }
+  for (int m = first; m < first + count; ++m) {
+    int16_t cur0[6], cur1[6];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+      cur0[b] = nx0[b];
+      cur1[b] = nx1[b];
+    }
+    if (m + 1 < first + count) {
+      const int16_t* zn = coef + (size_t)(m + 1) * 384;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        nx0[b] = zn[b * 64 + lane];
+        nx1[b] = zn[b * 64 + lane + 32];
       }
+    }
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+      const int which = b < 4 ? 0 : 1;
+      const int c0 = cur0[b], c1 = cur1[b];
       const uint32_t nz_lo = __ballot_sync(0xffffffffu, c0 != 0) | 1u;  // bit 0: the DC position bounds the first run
       const uint32_t nz_hi = __ballot_sync(0xffffffffu, c1 != 0);
       const uint64_t nz = ((uint64_t)nz_hi << 32) | nz_lo;
@@ -508,60 +525,56 @@ __global__ void __launch_bounds__(kEntropyWarps * 32) jpeg_entropy_kernel(const 
   }
   if (lane == 0) lens[i] = (int32_t)out;
   }
-  // The CTA that finishes last places the intervals in the stream (what a separate scan kernel would do):
-  // offsets[i] = header + sum of the earlier intervals and their 2-byte markers; status[0] = total bytes of
-  // the JPEG, status[1] = 1 if an interval overflowed its slot; status[2] is the arrival counter (left at 0).
-  __shared__ uint32_t part[kEntropyWarps * 32];
-  __shared__ int is_last, bad;
+  // What this CTA's intervals add to the stream (their bytes + one 2-byte marker each): the gather kernel
+  // sums these per-CTA totals instead of scanning 4 000 interval lengths.
+  __shared__ uint32_t sh_cta_bytes;
+  if (threadIdx.x == 0) sh_cta_bytes = 0u;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    is_last = atomicAdd(&status[2], 1u) == gridDim.x - 1u;
-    bad = 0;
+  if (lane == 0 && i < g.n_intervals) {
+    const int32_t n = lens[i];
+    if (n < 0) atomicOr(&status[1], 1u);  // the interval overflowed its slot: the host fails the frame
+    atomicAdd(&sh_cta_bytes, (uint32_t)max(n, 0) + 2u);
   }
   __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  constexpr int kT = kEntropyWarps * 32;
-  const int tid = threadIdx.x;
-  const int per = (g.n_intervals + kT - 1) / kT, lo = tid * per, hi = min(lo + per, g.n_intervals);
-  const volatile int32_t* vl = lens;
-  uint32_t sum = 0;
-  for (int k = lo; k < hi; ++k) {
-    const int32_t n = vl[k];
-    if (n < 0) bad = 1;
-    sum += (uint32_t)max(n, 0) + 2u;
-  }
-  part[tid] = sum;
-  __syncthreads();
-  for (int d = 1; d < kT; d <<= 1) {  // Hillis-Steele inclusive scan
-    const uint32_t v = tid >= d ? part[tid - d] : 0u;
-    __syncthreads();
-    part[tid] += v;
-    __syncthreads();
-  }
-  uint32_t at = (uint32_t)g.header_bytes + (tid ? part[tid - 1] : 0u);
-  for (int k = lo; k < hi; ++k) {
-    offsets[k] = at;
-    at += (uint32_t)max(vl[k], 0) + 2u;
-  }
-  if (tid == kT - 1) {
-    status[0] = (uint32_t)g.header_bytes + part[kT - 1];
-    status[1] = (uint32_t)bad;
-    status[2] = 0u;
-  }
+  if (threadIdx.x == 0) cta_bytes[blockIdx.x] = sh_cta_bytes;
 }
 
-__global__ void __launch_bounds__(256) jpeg_gather_kernel(Geometry g, const uint8_t* __restrict__ slots,
-                                                          const int32_t* __restrict__ lens,
-                                                          const uint32_t* __restrict__ offsets, uint8_t* __restrict__ out,
-                                                          size_t cap) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// One warp per interval, launched with the entropy kernel's grid: the CTA sums the byte totals of the CTAs
+// before it (its place in the stream), its warps take their intervals in order, each copies its slot and
+// appends the RSTm / EOI marker.  status[0] = total bytes of the JPEG (written by the last CTA).
+__global__ void __launch_bounds__(kEntropyWarps * 32) jpeg_gather_kernel(Geometry g, const uint8_t* __restrict__ slots,
+                                                                        const int32_t* __restrict__ lens,
+                                                                        const uint32_t* __restrict__ cta_bytes,
+                                                                        uint8_t* __restrict__ out, uint32_t* status,
+                                                                        size_t cap) {
+  __shared__ uint32_t sh_warp_sum[kEntropyWarps], sh_base, sh_off[kEntropyWarps + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t sum = 0;
+  for (int k = threadIdx.x; k < (int)blockIdx.x; k += blockDim.x) sum += cta_bytes[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) sh_warp_sum[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t at = (uint32_t)g.header_bytes;
+    for (int w = 0; w < kEntropyWarps; ++w) at += sh_warp_sum[w];
+    sh_base = at;
+    for (int w = 0; w < kEntropyWarps; ++w) {
+      sh_off[w] = at;
+      const int k = blockIdx.x * kEntropyWarps + w;
+      if (k < g.n_intervals) at += (uint32_t)max(lens[k], 0) + 2u;
+    }
+    sh_off[kEntropyWarps] = at;
+    if (blockIdx.x == gridDim.x - 1) status[0] = at;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * kEntropyWarps + warp;
   if (i >= g.n_intervals) return;
+  const uint32_t offset = sh_off[warp];
   const int n = max(lens[i], 0);
-  if ((size_t)offsets[i] + n + 2 > cap) return;  // the host sees total > cap in the status word and fails the frame
+  if ((size_t)offset + n + 2 > cap) return;  // the host sees total > cap in the status word and fails the frame
   const uint8_t* src = slots + (size_t)i * g.ri * kSlotBytesPerMcu;
-  uint8_t* dst = out + offsets[i];
+  uint8_t* dst = out + offset;
   for (int k = lane; k < n; k += 32) dst[k] = src[k];
   if (lane == 0) {
     dst[n] = 0xFF;

@@ -305,7 +305,7 @@ struct JpegSlot {
   int16_t* d_coef = nullptr;
   uint8_t* d_slots = nullptr;
   int32_t* d_lens = nullptr;
-  uint32_t* d_offsets = nullptr;
+  uint32_t* d_offsets = nullptr;  // per entropy-kernel CTA: bytes its intervals add to the stream
   uint8_t* d_out = nullptr;    // [0, 8): status (total bytes, overflow flag); the JPEG starts at byte 16
   uint8_t* h_out = nullptr;    // pinned mirror of d_out
   bh8_hud_line* d_hud = nullptr;
@@ -413,13 +413,16 @@ int jpeg_encode_async(bh8_sink* s, JpegSlot& js, void* d_bgr, cudaStream_t st, c
         static_cast<uint8_t*>(d_bgr), s->height, s->width, js.d_hud, s->hud_dev.glyph, s->hud_dev.advance);
   }
   BH8_SINK_CUDA(s, cudaEventRecord(ev0, st));
-  bh8jpeg::jpeg_transform_kernel<<<g.n_mcus, 64, 0, st>>>(static_cast<const uint8_t*>(d_bgr), s->d_tables, g, js.d_coef);
+  bh8jpeg::jpeg_transform_kernel<<<g.n_mcus, 64, 0, st>>>(static_cast<const uint8_t*>(d_bgr), s->d_tables, g, js.d_coef,
+                                                           reinterpret_cast<uint32_t*>(js.d_out));
   const size_t bit_smem = static_cast<size_t>(bh8jpeg::kEntropyWarps) * g.ri * bh8jpeg::kBitWordsPerMcu * sizeof(uint32_t);
   bh8jpeg::jpeg_entropy_kernel<<<(g.n_intervals + bh8jpeg::kEntropyWarps - 1) / bh8jpeg::kEntropyWarps,
                                  bh8jpeg::kEntropyWarps * 32, bit_smem, st>>>(s->d_tables, g, js.d_coef, js.d_slots, js.d_lens,
                                                                               js.d_offsets, reinterpret_cast<uint32_t*>(js.d_out));
-  bh8jpeg::jpeg_gather_kernel<<<(g.n_intervals * 32 + 255) / 256, 256, 0, st>>>(g, js.d_slots, js.d_lens, js.d_offsets,
-                                                                              js.d_out + kJpegOutPrefix, js.cap);
+  bh8jpeg::jpeg_gather_kernel<<<(g.n_intervals + bh8jpeg::kEntropyWarps - 1) / bh8jpeg::kEntropyWarps,
+                                bh8jpeg::kEntropyWarps * 32, 0, st>>>(g, js.d_slots, js.d_lens, js.d_offsets,
+                                                                      js.d_out + kJpegOutPrefix,
+                                                                      reinterpret_cast<uint32_t*>(js.d_out), js.cap);
   BH8_SINK_CUDA(s, cudaGetLastError());
   BH8_SINK_CUDA(s, cudaEventRecord(ev1, st));
   s->ctx->launches += s->hud.empty() ? 3 : 4;

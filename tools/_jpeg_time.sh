@@ -5,7 +5,7 @@ import csv
 rows=[r for r in csv.reader(open("gpurun_out/jpeg_t.csv")) if len(r)>10]
 h=rows[0]
 print("ri", $ri)
-for r in rows[4:7]:
+for r in rows[3:6]:
     d=dict(zip(h,r)); print(" ", d["Kernel Name"][:30], d["Metric Value"], d["Metric Unit"])
 PY
 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
