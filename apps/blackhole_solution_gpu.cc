@@ -7,7 +7,8 @@
 //
 //   blackhole_solution_gpu [--cfg N] [--width W] [--height H] [--frames K] [--nstep S]
 //                          [--texdir DIR] [--out PREFIX] [--video FILE.avi] [--script] [--hud]
-// --hud: the reference's HUD text (:309-326) is drawn into the frames written with --out.
+// --hud: the reference's HUD text (:309-326) is drawn into the frames written with --out (on the host) and
+// into the frames of --video (on the device, before the encode).
 // --script: the frame loop's tail (camera script + disc spin) is recorded as a blackhole::gpu::Script and
 // replayed on the GPU; frames are drawn from the device-resident script instead of host snapshots.
 // Writes PREFIX_<frame>.bgr (raw: int32 rows, int32 cols, BGR bytes) when --out is given, and a
@@ -87,7 +88,10 @@ int main(int argc, char** argv) {
     }
     for (int k = 0; k < frames; ++k) {
       const auto t1 = std::chrono::high_resolution_clock::now();
-      if (out_capture) out_capture->Write(manager, *scene->blackhole, scene->camera, nstep);
+      if (out_capture) {
+        if (hud) out_capture->SetHud(scene->camera);  // :309-326 come before out_capture.write(), :334
+        out_capture->Write(manager, *scene->blackhole, scene->camera, nstep);
+      }
       if (!out_capture || !out.empty()) gpu.Render(manager, *scene->blackhole, scene->camera, &screen, nstep);
       const auto t2 = std::chrono::high_resolution_clock::now();
       const auto us = std::chrono::duration_cast<std::chrono::microseconds>(t2 - t1).count();

@@ -774,11 +774,16 @@ int bh8_sink_merge(const char* const* part_paths, int n_parts, const char* out_p
   if (!out.open(out_path, parts[0].width(), parts[0].height(), parts[0].fps(), &err))
     return fail(nullptr, BH8_EINVAL, "bh8_sink_merge: " + err);
   std::vector<uint8_t> buf;
+  const auto give_up = [&]() {  // no half-written video is left behind
+    out.abandon();
+    std::remove(out_path);
+    if (file_bytes) *file_bytes = 0;
+    return fail(nullptr, BH8_EINVAL, "bh8_sink_merge: " + err);
+  };
   for (uint64_t k = 0; k < total; ++k) {
-    if (!parts[k % n_parts].read(k / n_parts, &buf, &err) || !out.append(buf.data(), buf.size(), &err))
-      return fail(nullptr, BH8_EINVAL, "bh8_sink_merge: " + err);
+    if (!parts[k % n_parts].read(k / n_parts, &buf, &err) || !out.append(buf.data(), buf.size(), &err)) return give_up();
   }
-  if (!out.close(file_bytes, &err)) return fail(nullptr, BH8_EINVAL, "bh8_sink_merge: " + err);
+  if (!out.close(file_bytes, &err)) return give_up();
   if (frames) *frames = total;
   return BH8_OK;
 }

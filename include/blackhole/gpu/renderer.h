@@ -138,8 +138,9 @@ class Renderer {
 // FONT_HERSHEY_PLAIN text -- camera position, basis vectors, field of view -- drawn into the frame after
 // rendering.  bh8_draw_text reproduces cv::putText's pixels bit for bit, so this is a drop-in for that block
 // on frames that came back to the host.  Returns the lines it drew.
+// The five strings of that block, formatted as the reference formats them (operator<< of cv::Vec3d).
 template <typename T>
-std::vector<std::string> DrawHud(const Camera<T>& camera, cv::Mat* frame) {
+std::vector<std::string> HudLines(const Camera<T>& camera) {
   std::vector<std::string> lines;
   const auto add = [&](const char* label, const auto& value, const char* suffix = "") {
     std::stringstream ss;
@@ -151,6 +152,12 @@ std::vector<std::string> DrawHud(const Camera<T>& camera, cv::Mat* frame) {
   add("VectorY: ", camera.vector_y());
   add("VectorZ: ", camera.vector_z());
   add("FoV: ", camera.fov() * 180.0 / blackhole::pi, " deg");
+  return lines;
+}
+
+template <typename T>
+std::vector<std::string> DrawHud(const Camera<T>& camera, cv::Mat* frame) {
+  const std::vector<std::string> lines = HudLines(camera);
   for (size_t k = 0; k < lines.size(); ++k)  // {0, 10}, {0, 25}, {0, 40}, {0, 55}, {0, 70}
     bh8_draw_text(frame->data, frame->rows, frame->cols, static_cast<size_t>(frame->cols) * 3, 0,
                   10 + 15 * static_cast<int>(k), lines[k].c_str(), 0, 255, 0);
@@ -285,6 +292,26 @@ class VideoWriter {
     if (bh8_sink_render(sink_, &scene, &cam, &prm) != BH8_OK)
       throw std::runtime_error(std::string("bh8_sink_render: ") + bh8_sink_last_error(sink_));
   }
+
+  // The reference draws its HUD into the frame BEFORE out_capture.write (blackhole_solution_test.cc:309-334):
+  // the frames written from now on carry these lines, drawn on the device before the encode.  Call it again
+  // when the camera has moved; HudOff() stops it.
+  template <typename T>
+  void SetHud(const Camera<T>& camera) {
+    const std::vector<std::string> text = HudLines(camera);
+    std::vector<bh8_hud_line> lines(text.size());
+    for (size_t k = 0; k < text.size(); ++k) {
+      bh8_hud_line& ln = lines[k];
+      std::memset(&ln, 0, sizeof ln);
+      ln.x = 0;
+      ln.y = 10 + 15 * static_cast<int>(k);
+      ln.g = 255;
+      std::strncpy(ln.text, text[k].c_str(), BH8_HUD_MAX_TEXT - 1);
+    }
+    if (bh8_sink_hud(sink_, lines.data(), static_cast<int>(lines.size())) != BH8_OK)
+      throw std::runtime_error(std::string("bh8_sink_hud: ") + bh8_sink_last_error(sink_));
+  }
+  void HudOff() { bh8_sink_hud(sink_, nullptr, 0); }
 
   // Pipelined Write(): returns once the frame is queued; frame k+1 is traced while frame k is encoded.
   template <typename T>
