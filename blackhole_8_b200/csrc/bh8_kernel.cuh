@@ -40,8 +40,16 @@ static_assert(kPatchW * kPatchH == 32 && kTileH % kPatchH == 0, "a warp must til
 constexpr int kMaxFilterPlanes = kMaxFilterSlots;
 constexpr int kFineNstep = 64;  // from here on the kernel takes 3 updates per round of votes instead of 2
 #ifndef BH8_MIN_BLOCKS
-#define BH8_MIN_BLOCKS 5  // CTAs per SM the register allocation is sized for (measured best of 2..5 on B200)
+#define BH8_MIN_BLOCKS 5  // CTAs per SM the register allocation is sized for (48 registers; measured best of 3..6 on B200)
 #endif
+// The mailbox is 88 + 4 (10 + 2 NN) bytes per ray, so up to NN = 1 SIX CTAs would fit the SM's shared memory
+// at 40 registers (-DBH8_MIN_BLOCKS=6).  Measured: 2 % slower than five at 48 (0.1638 vs 0.1607 ms) -- the
+// spill code of the 40-register build costs more instructions than the extra eight warps hide; issue slots
+// stay 79 % busy either way.  Four CTAs (dummy shared memory, same registers): 3.7 % slower.
+template <int NN>
+struct MinBlocks {
+  static constexpr int value = (NN >= 2 && BH8_MIN_BLOCKS > 5) ? 5 : BH8_MIN_BLOCKS;
+};
 
 struct Bh8Tex {
   unsigned long long obj[BH8_MAX_TEXTURES];
@@ -162,7 +170,7 @@ struct SchedCount {
 };
 
 // One 8x4-pixel patch, all 32 lanes of the warp: ray setup, then stepping phases and exact passes in turn
-// until every ray of the patch has ended.  The result waits in each lane's mailbox (kMwSteps, kMwHit,
+// until every ray of the patch has ended.  The result waits in each lane's mailbox (mail_steps, mail_hit,
 // kMwBgr, kMwOob).
 template <int NN, bool STATS, int UPV>
 __device__ __forceinline__ void trace_patch(const Bh8Frame& f, const DeviceFetch& fetch, const Mail mail,
@@ -197,9 +205,10 @@ __device__ __forceinline__ void trace_patch(const Bh8Frame& f, const DeviceFetch
 }
 
 // Mailbox of this thread + the warp's copy of the stepping constants (StepConst) in shared memory.
+template <int NN>
 __device__ __forceinline__ Mail make_mail(const Bh8Frame& f, int tid, int lane, int warp, uint32_t* sc_addr) {
   __shared__ double sh_md[kMailDoubles * kThreads];
-  __shared__ int sh_mi[kMailInts * kThreads];
+  __shared__ int sh_mi[MailInts<NN>::value * kThreads];
   __shared__ double sh_step_const[kThreads / 32][2];
   Mail mail;
 #if defined(__CUDA_ARCH__)
@@ -254,7 +263,7 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
   const bool inside = x < f.width && y < f.height;
 
   uint32_t sc_addr;
-  const Mail mail = make_mail(f, tid, lane, warp, &sc_addr);
+  const Mail mail = make_mail<NN>(f, tid, lane, warp, &sc_addr);
 #if defined(BH8_DUMMY_SMEM)  // occupancy experiment: shared memory nobody uses, to run 4 instead of 5 CTAs per SM
   __shared__ volatile char sh_dummy[BH8_DUMMY_SMEM];
   if (f.width < 0) sh_dummy[tid] = 1;
@@ -264,8 +273,8 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
   trace_patch<NN, STATS, UPV>(f, fetch, mail, sc_addr, x, y, inside, n);
 
   // ---- colour: lane_exact left it in the mailbox when the ray hit -----------------------------------
-  const int steps = inside ? mail.get_w(kMwSteps) : 0;
-  const int hit_obj = inside ? mail.get_w(kMwHit) : -1;
+  const int steps = inside ? mail_steps(mail) : 0;
+  const int hit_obj = inside ? mail_hit(mail) : -1;
   const uint32_t bgr = hit_obj >= 0 ? (uint32_t)mail.get_w(kMwBgr) : 0u;
   const uint32_t oob = hit_obj >= 0 ? (uint32_t)mail.get_w(kMwOob) : 0u;
   int cls = BH8_CLASS_BACKGROUND, key = -1;
@@ -298,7 +307,7 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
 }
 
 template <int NN, bool STATS, int UPV>
-__global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, MinBlocks<NN>::value)
 bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
   render_tile<NN, STATS, UPV>(f, tex, out);
 }
@@ -316,7 +325,7 @@ __device__ __forceinline__ void render_warps(const Bh8Frame& f, const Bh8Tex& te
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   uint32_t sc_addr;
-  const Mail mail = make_mail(f, tid, lane, warp, &sc_addr);
+  const Mail mail = make_mail<NN>(f, tid, lane, warp, &sc_addr);
   const DeviceFetch fetch{tex};
 
   // per-warp totals for the optional counters (added to out.stats once, when the warp leaves)
@@ -349,8 +358,8 @@ __device__ __forceinline__ void render_warps(const Bh8Frame& f, const Bh8Tex& te
     trace_patch<NN, STATS, UPV>(f, fetch, mail, sc_addr, x, y, inside, n);
 
     if (inside) {  // a warp stores its own patch: four 32-byte row segments (4-byte formats)
-      const int steps = mail.get_w(kMwSteps);
-      const int hit_obj = mail.get_w(kMwHit);
+      const int steps = mail_steps(mail);
+      const int hit_obj = mail_hit(mail);
       const uint32_t bgr = hit_obj >= 0 ? (uint32_t)mail.get_w(kMwBgr) : 0u;
       int cls = BH8_CLASS_BACKGROUND, key = -1;
       if (hit_obj >= 0) {
@@ -408,7 +417,7 @@ __device__ __forceinline__ void render_warps(const Bh8Frame& f, const Bh8Tex& te
 }
 
 template <int NN, bool STATS, int UPV>
-__global__ void __launch_bounds__(kThreads, BH8_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, MinBlocks<NN>::value)
 bh8_render_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh8Tex tex, const Bh8Out out) {
   render_warps<NN, STATS, UPV>(f, tex, out);
 }

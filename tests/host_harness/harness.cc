@@ -59,7 +59,7 @@ static void trace_frame(const Bh8Frame& f, const HostFetch& fetch, uint8_t* out_
         }
       }
       for (int k = 0; k < g_frozen_updates; ++k) bh8::lane_update(f, L, mail, bh8::StepConst::load(f));  // ended rays too
-      const int hit_obj = mail.get_w(bh8::kMwHit);
+      const int hit_obj = bh8::mail_hit(mail);
       const uint32_t bgr = hit_obj >= 0 ? (uint32_t)mail.get_w(bh8::kMwBgr) : 0u;
       int cls = BH8_CLASS_BACKGROUND, key = -1;
       if (hit_obj >= 0) {
@@ -72,7 +72,7 @@ static void trace_frame(const Bh8Frame& f, const HostFetch& fetch, uint8_t* out_
       out_bgr[3 * i + 2] = (bgr >> 16) & 255;
       out_class[i] = (uint8_t)cls;
       out_key[i] = (int8_t)key;
-      out_steps[i] = (uint16_t)mail.get_w(bh8::kMwSteps);
+      out_steps[i] = (uint16_t)bh8::mail_steps(mail);
     }
   }
 }
@@ -222,7 +222,7 @@ static void trace_frame_warps(const Bh8Frame& f, const HostFetch& fetch, int upd
       for (int l = 0; l < kLanes; ++l) {
         if (!inside[l]) continue;
         const int x = px0 + (l % kPW), y = py0 + (l / kPW);
-        const int hit_obj = mail[l].get_w(bh8::kMwHit);
+        const int hit_obj = bh8::mail_hit(mail[l]);
         const uint32_t bgr = hit_obj >= 0 ? (uint32_t)mail[l].get_w(bh8::kMwBgr) : 0u;
         const size_t i = static_cast<size_t>(y) * f.width + x;
         out_bgr[3 * i] = bgr & 255;
@@ -230,7 +230,7 @@ static void trace_frame_warps(const Bh8Frame& f, const HostFetch& fetch, int upd
         out_bgr[3 * i + 2] = (bgr >> 16) & 255;
         out_class[i] = (uint8_t)(hit_obj >= 0 ? f.obj[hit_obj].cls : BH8_CLASS_BACKGROUND);
         out_key[i] = (int8_t)(hit_obj >= 0 ? f.obj[hit_obj].key : -1);
-        out_steps[i] = (uint16_t)mail[l].get_w(bh8::kMwSteps);
+        out_steps[i] = (uint16_t)bh8::mail_steps(mail[l]);
       }
     }
   }
