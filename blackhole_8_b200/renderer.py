@@ -359,7 +359,7 @@ class VideoSink:
     """Motion-JPEG AVI writer, the mirror of include/bh8.h's bh8_sink_* (SURVEY 8f-2): stands where the
     reference's cv::VideoWriter(path, fourcc('M','J','P','G'), fps, size) stands
     (blackhole_solution_test.cc:71-72,334).  With a Renderer the frames are encoded on the GPU
-    (nvJPEG) from the device-resident frame; with renderer=None it is a plain container for ready
+    (own JPEG kernels) from the device-resident frame; with renderer=None it is a plain container for ready
     JPEGs (no GPU needed)."""
 
     def __init__(self, renderer, path, width, height, fps=29.0, quality=95):

@@ -275,7 +275,7 @@ int bh8_sink_write_device(bh8_sink* sink, const void* d_bgr_frame);
 int bh8_sink_append_jpeg(bh8_sink* sink, const uint8_t* jpeg, size_t bytes);
 /* Bitstream of the most recent frame; valid until the next call on this sink. */
 int bh8_sink_last_jpeg(bh8_sink* sink, const uint8_t** data, size_t* bytes);
-/* Frames so far, their JPEG bytes, and the device time nvJPEG took for them (CUDA events, ms). */
+/* Frames so far, their JPEG bytes, and the device time the encoder took for them (CUDA events, ms). */
 int bh8_sink_stats(const bh8_sink* sink, uint64_t* frames, uint64_t* jpeg_bytes, double* encode_ms);
 const char* bh8_sink_last_error(const bh8_sink* sink);
 /* Finish the AVI (index, sizes), release everything; the handle is invalid afterwards. */

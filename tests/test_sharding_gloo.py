@@ -44,7 +44,7 @@ def _worker(rank, world, port, mode, out_path):
                         frame[r0:r1] = b[r0:r1]
                 np.save(out_path, frame.numpy())
         elif mode == "video":
-            # one sink per rank on its own frames (the GPU ranks encode with nvJPEG; here cv2 stands in),
+            # one sink per rank on its own frames (the GPU ranks encode on the device; here cv2 stands in),
             # then rank 0 merges the per-rank files into ONE video in frame order (bh8_sink_merge)
             import cv2
             from blackhole_8_b200.renderer import VideoSink, merge_video_parts

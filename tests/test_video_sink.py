@@ -5,7 +5,7 @@ A JPEG stream cannot be byte-identical between encoders, so parity here means wh
 reference's video.avi relies on: the file is a valid MJPG AVI that OpenCV itself reads back with the
 right frame count, size and rate, and every decoded frame matches the rendered frame as closely as
 OpenCV's own JPEG encoder at the same quality does (PSNR, stated below).
-CPU tests cover the container (fed with JPEGs from cv2.imencode); the `gpu` tests the nvJPEG path."""
+CPU tests cover the container (fed with JPEGs from cv2.imencode); the `gpu` tests the device encoder (own kernels) and the HUD blit."""
 import os
 import struct
 
