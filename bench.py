@@ -719,7 +719,7 @@ def main():
     ap.add_argument("--kernel-only", action="store_true",
                     help="tuning runs: skip the e2e / sink / script / CPU legs (their keys are null; not a driver line)")
     ap.add_argument("--workload", default="cfg1_spin",
-                    choices=["cfg1_spin", "cfg3_flythrough", "cfg1_static", "cfg10_flat", "cfg4_8k"],
+                    choices=["cfg1_spin", "cfg3_flythrough", "cfg1_static", "cfg2_static", "cfg10_flat", "cfg4_8k"],
                     help="frame sequence: configs[1] with the disc spinning frame to frame as in the "
                          "reference's loop (default), the configs[3] fly-through, or configs[1] frame 0 only")
     args = ap.parse_args()
@@ -772,6 +772,10 @@ def main():
     # N, no data-path collective.
     from blackhole_8_b200 import sharding
     if args.workload == "cfg1_static":
+        seq = [base]
+    elif args.workload == "cfg2_static":  # configs[2]: the hole among ordinary textured objects and a chess floor
+        base = load_snapshot("cfg2_1920x1080")
+        r.set_textures(base, load_texture)
         seq = [base]
     elif args.workload == "cfg10_flat":  # the ray_tracer_test.cc scene (linear tracer) at 1080p
         base = load_snapshot("cfg10_flat_800x450").with_resolution(W, H)
