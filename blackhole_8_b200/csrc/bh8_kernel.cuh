@@ -188,19 +188,23 @@ __device__ __forceinline__ void trace_patch(const Bh8Frame& f, const DeviceFetch
     // only: nothing of the warp's bookkeeping is carried across the exact pass.
     int waited = 0, todo;
     const StepConst sc = StepConst::load_shared(sc_addr);
-    do {
+    for (;;) {
 #pragma unroll
       for (int k = 0; k < UPV; ++k) lane_update(f, L, mail, sc);
       if (STATS) ++sc_n.n_iter;
       const unsigned present = __reduce_or_sync(0xffffffffu, (unsigned)L.state);
+      if (present == (unsigned)kRun) continue;  // the usual round: nobody waits (ended lanes are state 0)
       todo = warp_decide(present, waited, f.resolve_wait);
-    } while (todo == kWarpStep);
+      if (todo != kWarpStep) break;
+    }
     if (todo == kWarpDone) break;  // every ray of the patch has ended
     if (STATS) {
       ++sc_n.n_pass;
       if (L.state & (kPend | kPendChord)) ++sc_n.n_test;
     }
-    lane_resolve(f, L, mail, fetch);  // all 32 lanes together; it colours the rays that end
+    // All 32 lanes together; it colours the rays that end.  The usual pass is the last one (every ray of
+    // the patch met something): no further round then.
+    if (!lane_resolve(f, L, mail, fetch)) break;
   }
 }
 

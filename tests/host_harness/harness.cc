@@ -10,8 +10,25 @@
 
 #define BH8_HOST_COUNTERS 1
 static unsigned long long bh8_host_filter_evaluations = 0;  // bumped by side_filter()
+// Which parts of lane_update_rare() the updates entered (BH8_TRACE): per lane, and per update slot of the
+// emulated warp (a slot counts once however many of its lanes went in -- what the warp pays for).
+static unsigned long long g_trace_lane[16] = {0}, g_trace_slot[16] = {0};
+static unsigned g_trace_mask[8] = {0};
+static int g_trace_k = 0;
+static inline void bh8_host_trace(int reason) {
+  ++g_trace_lane[reason];
+  g_trace_mask[g_trace_k] |= 1u << reason;
+}
 #include "bh8_ray.cuh"
 #include "bh8_warp.cuh"
+
+extern "C" void bh8_harness_take_trace(unsigned long long* per_lane, unsigned long long* per_slot) {
+  for (int r = 0; r < 16; ++r) {
+    per_lane[r] = g_trace_lane[r];
+    per_slot[r] = g_trace_slot[r];
+    g_trace_lane[r] = g_trace_slot[r] = 0;
+  }
+}
 
 extern "C" unsigned long long bh8_harness_take_filter_evaluations() {
   const unsigned long long n = bh8_host_filter_evaluations;
@@ -55,7 +72,7 @@ static void trace_frame(const Bh8Frame& f, const HostFetch& fetch, uint8_t* out_
           // warp attends to it: they must not change anything.
           for (int k = 0; k < g_frozen_updates; ++k) bh8::lane_update(f, L, mail, bh8::StepConst::load(f));
           counters[1]++;
-          bh8::lane_resolve(f, L, mail, fetch);
+          if (!bh8::lane_resolve(f, L, mail, fetch)) break;  // ended: the lane is not loaded back
         }
       }
       for (int k = 0; k < g_frozen_updates; ++k) bh8::lane_update(f, L, mail, bh8::StepConst::load(f));  // ended rays too
@@ -208,15 +225,27 @@ static void trace_frame_warps(const Bh8Frame& f, const HostFetch& fetch, int upd
       for (uint64_t round = 0;; ++round) {
         unsigned present = 0;
         for (int l = 0; l < kLanes; ++l) {
-          for (int k = 0; k < updates_per_vote; ++k) bh8::lane_update(f, L[l], mail[l], bh8::StepConst::load(f));
+          for (int k = 0; k < updates_per_vote; ++k) {
+            g_trace_k = k & 7;
+            bh8::lane_update(f, L[l], mail[l], bh8::StepConst::load(f));
+          }
           present |= (unsigned)L[l].state;
         }
+        for (int k = 0; k < 8; ++k) {
+          for (int r = 0; r < 16; ++r) g_trace_slot[r] += (g_trace_mask[k] >> r) & 1u;
+          g_trace_mask[k] = 0;
+        }
+        g_trace_k = 0;
         counters[0] += (uint64_t)updates_per_vote;  // update slots of this warp
         const int todo = bh8::warp_decide(present, waited, f.resolve_wait);
         if (todo == bh8::kWarpStep) continue;
         if (todo == bh8::kWarpDone) break;
         counters[1]++;  // resolve passes
-        for (int l = 0; l < kLanes; ++l) bh8::lane_resolve(f, L[l], mail[l], fetch);  // ALL lanes, as in the kernel
+        bool alive = false;
+        for (int l = 0; l < kLanes; ++l) {
+          alive = bh8::lane_resolve(f, L[l], mail[l], fetch) || alive;  // ALL lanes, as in the kernel
+        }
+        if (!alive) break;  // the usual pass is the last one: no further round (trace_patch)
         if (round > 100000000ull) return;  // a warp that never ends would hang the GPU: leave zeros, the test fails
       }
       for (int l = 0; l < kLanes; ++l) {
