@@ -277,15 +277,9 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
   trace_patch<NN, STATS, UPV>(f, fetch, mail, sc_addr, x, y, inside, n);
 
   // ---- colour: lane_exact left it in the mailbox when the ray hit -----------------------------------
-  const int steps = inside ? mail_steps(mail) : 0;
-  const int hit_obj = inside ? mail_hit(mail) : -1;
+  const uint32_t result = inside ? (uint32_t)mail.get_w(kMwFlags) : 0u;  // flags | steps << 8 | (hit + 1) << 24
+  const int hit_obj = (int)(result >> 24) - 1;
   const uint32_t bgr = hit_obj >= 0 ? (uint32_t)mail.get_w(kMwBgr) : 0u;
-  const uint32_t oob = hit_obj >= 0 ? (uint32_t)mail.get_w(kMwOob) : 0u;
-  int cls = BH8_CLASS_BACKGROUND, key = -1;
-  if (hit_obj >= 0) {
-    cls = f.obj[hit_obj].cls;
-    key = f.obj[hit_obj].key;
-  }
   // Plain launches (no maps, no counters): every warp stores its own patch the moment it is done -- four
   // 32-byte row segments for the 4-byte formats, 24-byte ones for BGR8 -- and leaves; no CTA barrier, no
   // staging tile (+1.5 % over the tile path on B200, which the launches with maps / counters still take).
@@ -305,6 +299,13 @@ __device__ __forceinline__ void render_tile(const Bh8Frame& f, const Bh8Tex& tex
       }
     }
     return;
+  }
+  const int steps = (int)((result >> 8) & 0xFFFFu);
+  const uint32_t oob = hit_obj >= 0 ? (uint32_t)mail.get_w(kMwOob) : 0u;
+  int cls = BH8_CLASS_BACKGROUND, key = -1;
+  if (hit_obj >= 0) {
+    cls = f.obj[hit_obj].cls;
+    key = f.obj[hit_obj].key;
   }
   store_pixel(f, out, sh_rgba, sh_red, tid, lane, slot, x0, y0, x, y, inside, bgr, oob, cls, key, steps,
               n.n_iter * UPV, n.n_pass, n.n_test);
