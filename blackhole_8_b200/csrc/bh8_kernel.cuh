@@ -470,11 +470,12 @@ bh8_linear_kernel(const __grid_constant__ Bh8Frame f, const __grid_constant__ Bh
   linear_tile(f, tex, out);
 }
 
-// Precision study: the bare geodesic update chain (u += du; G; rsqrt; trapezoid; two compares) for
-// `updates` steps per thread, in FP64 exactly as lane_update runs it, or in FP32 (FFMA + MUFU.RSQ).
-// Nothing else of the renderer is in here: it isolates what the choice of precision can buy for
-// the stepping loop.  Each thread gets its own impact parameter so the compiler
-// cannot share work; the result is folded into a checksum the host ignores.
+// Precision study / stepping yardstick: the bare geodesic update chain for `updates` steps per thread --
+// in FP64 the very operations of lane_advance() and lane_update()'s tests (11 FP64 instructions + MUFU.RSQ64H,
+// the two triggers compared on high words), or the same chain in FP32 (FFMA + MUFU.RSQ).  Nothing else of
+// the renderer is in here: it isolates what the stepping loop costs and what the choice of precision can
+// buy for it.  Each thread gets its own impact parameter so the compiler cannot share
+// work; the result is folded into a checksum the host ignores.
 template <typename Real>
 __global__ void __launch_bounds__(256, 5)
 bh8_stepping_probe_kernel(double* sink, int updates, double two_m, double u0, double du, double binv2_0) {
@@ -482,21 +483,34 @@ bh8_stepping_probe_kernel(double* sink, int updates, double two_m, double u0, do
   Real u = (Real)u0, phi = 0, dphi_prev = 0;
   const Real delta = (Real)(du * (1.0 + 1e-4 * (gid & 1023))), du_h = (Real)0.5 * delta;
   const Real binv2 = (Real)(binv2_0 * (1.0 + 1e-3 * (gid & 255))), tm = (Real)two_m;
-  const Real trig = (Real)1e30;
   int parked = 0;
-  for (int i = 0; i < updates; ++i) {
-    u += delta;
-    const Real g = fma(u * u, fma(tm, u, (Real)-1), binv2);
-    Real dphi;
-    if (sizeof(Real) == 8) {
-      dphi = (Real)fast_rsqrt((double)g);
-    } else {
-      dphi = (Real)rsqrtf((float)g);
+  if (sizeof(Real) == 8) {
+    StepConst sc;
+    sc.two_m = two_m;
+    sc.k375 = 0.375;
+    asm volatile("" : "+d"(sc.two_m), "+d"(sc.k375));  // registers, as StepConst::load_shared leaves them
+    const uint32_t t_thr = step_turn_threshold((double)du_h), trig_hi = trig_word(1e30);
+    double ud = (double)u, phid = 0.0, prev = 0.0;
+    for (int i = 0; i < updates; ++i) {
+      ud += (double)delta;
+      const double dphi = fast_rsqrt(fma(ud * ud, fma(sc.two_m, ud, -1.0), (double)binv2), sc.k375);
+      const double s = prev + dphi;
+      prev = dphi;
+      phid = fma(s, (double)du_h, phid);
+      if (hi_word(s) >= t_thr || hi_word(phid) >= trig_hi) ++parked;
     }
-    const Real t = (dphi_prev + dphi) * du_h;
-    dphi_prev = dphi;
-    phi += t;
-    if (!(t <= (Real)1) || !(phi < trig)) ++parked;
+    phi = (Real)phid;
+  } else {
+    const Real trig = (Real)1e30;
+    for (int i = 0; i < updates; ++i) {
+      u += delta;
+      const Real g = fma(u * u, fma(tm, u, (Real)-1), binv2);
+      const Real dphi = (Real)rsqrtf((float)g);
+      const Real s = dphi_prev + dphi;
+      dphi_prev = dphi;
+      phi = fma(s, du_h, phi);
+      if (!(s * du_h <= (Real)1) || !(phi < trig)) ++parked;
+    }
   }
   if (phi == (Real)123.456 || parked == updates + 1) sink[0] = (double)phi + parked;
 }
