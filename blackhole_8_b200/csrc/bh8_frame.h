@@ -73,6 +73,7 @@ struct Bh8Frame {
   // leases of filter (2), see lane_update: 0.4995 / max|n_j| and 0.24975 / max|c_bh_j| over the
   // non-central planes (the margin is split between the phi and the u movement, 0.1 % kept back)
   float lease_kphi, lease_ku;
+  float nc_max_n, nc_max_c;  // max|n_j|, max|c_bh_j| themselves (outbound leases use the whole margin, lane_update_rare)
   uint32_t nc_cam_bits;      // side of the camera w.r.t. non-central plane j: bit j = positive, bit 16+j = negative
   int32_t resolve_wait;      // warp iterations a pending exact test may wait for company (batching window)
   // output
@@ -338,6 +339,8 @@ BH8F_HD int bh8_build_frame_core(const bh8_scene* scene, const bh8_camera* cam, 
   }
   f->lease_kphi = f->noncentral_mask ? (float)BH8F_DIV(0.4995, max_n) : 0.0f;
   f->lease_ku = f->noncentral_mask ? (float)BH8F_DIV(0.24975, max_c) : 0.0f;
+  f->nc_max_n = f->noncentral_mask ? (float)max_n : 0.0f;
+  f->nc_max_c = f->noncentral_mask ? (float)max_c : 0.0f;
   // A chord between two points of the ray stays inside radius max(r1,r2); a plane at distance D
   // from the hole can only be met when max(r1,r2) >= D, i.e. min(u1,u2) <= 1/D (small margin).
   f->u_gate = f->noncentral_mask ? BH8F_DIV(BH8F_ADD(1.0, 1e-9), min_dist) : -1.0;
