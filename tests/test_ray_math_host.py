@@ -231,3 +231,22 @@ def test_flat_space_scene_may_contain_a_hole_as_a_black_sphere():
     d["objects"] = [dict(hole, key=10, v=[0.0, 300.0, 0.0] + [0.0] * 12)] + d["objects"]
     with pytest.raises(AssertionError, match="more than one black hole"):
         harness_render(abi.SceneSnapshot.from_dict(d))
+
+
+@pytest.mark.parametrize("name", ["cfg1_odd_333x187", "cfg2_640x360"])
+def test_step_counts_other_than_the_references(name):
+    """nstep is a parameter of the path (blackhole_solution_test.cc:202): the leg changes sit at nstep - 1,
+    nstep and 2 nstep - 1, adjacent for small nstep, and the turn's short step is taken inside its event
+    (lane_event, fuse).  Hit class and step count equal the oracle's for odd, tiny and large step counts,
+    one lane at a time and under the warp schedule."""
+    snap = O.load_golden(name)["snap"]
+    for n in (2, 3, 7, 33):
+        ref = O.render(snap, nstep=n)
+        one = harness_render(snap, nstep=n)
+        got = harness_render_warps(snap, nstep=n)
+        for k in ("bgr", "cls", "key", "steps"):
+            assert np.array_equal(got[k], one[k]), (name, n, k)
+        assert np.array_equal(one["cls"], ref["cls"]), (name, n)
+        assert np.array_equal(one["steps"], ref["steps"]), (name, n)
+        off = np.abs(one["bgr"].astype(int) - ref["bgr"].astype(int)).max(axis=2) > 2
+        assert off.mean() <= 1e-3, (name, n, off.mean())  # north_star: RGB within 2/255 on >= 99.9 % of pixels
