@@ -72,6 +72,22 @@ def test_8k_fine_steps_tile_rows_match_oracle(G):
         print(rows, rep)
 
 
+@pytest.mark.parametrize("name", ["cfg1_odd_333x187", "cfg2_640x360"])
+def test_step_counts_other_than_the_references(G, name):
+    """nstep 3, 7, 33 (UPV 2) and 64, 100 (UPV 3): leg changes on adjacent steps, the fused turn, both
+    instantiations of the stepping loop -- against the oracle on the host cores."""
+    snap = O.load_golden(name)["snap"]
+    for n in (3, 7, 33, 64, 100):
+        ref = O.render(snap, nstep=n)
+        got = G.gpu_render(snap, nstep=n)
+        rep = parity.assert_parity(got, ref, "%s nstep %d" % (name, n))
+        assert rep["steps_agreement"] >= 0.999, (n, rep)
+        assert int(got["steps"].max()) <= 2 * n - 1
+        plain = G.gpu_render(snap, nstep=n, stats=False)
+        for k in ("bgr", "cls", "key", "steps"):
+            assert np.array_equal(plain[k], got[k]), (n, k)
+
+
 def test_pixel_formats_agree(G):
     g = O.load_golden("cfg1_odd_333x187")  # odd width: scalar store path
     a = G.gpu_render(g["snap"], pixel_format=abi.PIXEL_BGR8)
