@@ -579,11 +579,15 @@ def instruction_model():
         return None
     with open(files[-1]) as f:
         model = json.load(f)
-    h = hashlib.sha256()
+    import re
+    h = hashlib.sha256()  # the sources as the compiler sees them: no comments, no blank lines (tools/instr_model.py)
     src = os.path.join(ROOT, "blackhole_8_b200", "csrc")
     for n in model.get("sources", []):
-        with open(os.path.join(src, n), "rb") as f:
-            h.update(f.read())
+        with open(os.path.join(src, n)) as f:
+            text = f.read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        h.update("\n".join(ln.strip() for ln in text.splitlines() if ln.strip()).encode())
     model["file"] = os.path.relpath(files[-1], ROOT)
     model["matches_running_sources"] = h.hexdigest() == model.get("sources_sha256")
     return model

@@ -5,17 +5,18 @@
 //
 // Warp schedule.  A warp is an 8x4-pixel patch, so neighbouring rays end at neighbouring steps.
 // Every lane walks its own ray through ONE loop whose body is the lean geodesic update
-// (ray_advance: ~12 FP64 instructions); the step index is per-lane state, so lanes may drift apart.
-// A lane whose segment needs the exact object test (a plane crossing, a possible horizon hit) does
-// not run it on the spot -- that would serialise the warp once per distinct hit step -- but parks
-// (`pend`) while the other lanes keep stepping.  __ballot_sync() tells the warp who is parked and
-// who still runs; the exact tests (ray_resolve: sincos, 1/u, every object's Collide()) are executed
-// together once no lane is left running or the oldest has waited `resolve_wait` iterations, so the
-// expensive divergent section runs for many lanes at once.  Rays that end (hit, captured, escaped to
-// r ~ r0) drop out of the ballots; the loop leaves when __any_sync() finds no live lane, so a patch
-// that has finished early does not wait for anything.
-// Colour (texture object fetch / chess / black) goes into a shared RGBA tile that leaves as 16-byte
-// coalesced stores: 4 pixels per store, 128 B per tile row.
+// (lane_update: 11 FP64 instructions + MUFU.RSQ64H, three integer compares); the step index is per-lane
+// state, so lanes may drift apart.  A lane whose segment needs the exact object test (a plane crossing, a
+// possible horizon hit) does not run it on the spot -- that would serialise the warp once per distinct
+// hit step -- but freezes (kPend) while the other lanes keep stepping: its increments are zero, the update
+// leaves it where it is.  One __reduce_or_sync() of the lanes' states per round of UPV updates tells the
+// warp who waits and who still runs (the usual round -- everybody runs or has ended -- is one uniform
+// compare); the exact tests (lane_resolve: sincos, 1/u, the objects' Collide()) are executed by all 32
+// lanes together, on their mailboxes, once no lane is left running or the oldest has waited
+// `resolve_wait` rounds.  The pass colours the rays that end and tells whether any ray is still alive:
+// the usual pass is the last one and the warp leaves at once.
+// Plain launches store each warp's patch directly; launches with maps or counters go through a shared
+// RGBA tile that leaves as 16-byte coalesced stores.
 #ifndef BH8_KERNEL_CUH_
 #define BH8_KERNEL_CUH_
 

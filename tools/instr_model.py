@@ -19,7 +19,8 @@ With the executed counts of the capture this gives, per warp,
 (fixed = setup + rare + other at the captured workload) and the same for executed FP64 flops (DFMA 2, DMUL /
 DADD 1, per lane).  bench.py feeds the device-counted update slots and resolve passes of ITS run into the
 model: the line's `issue_bound_frac` and the fixed part of the executed flops come from here, marked as taken
-from a committed capture, and are used only while the kernel sources still hash to `sources_sha256`."""
+from a committed capture, and are used only while the kernel sources still hash to `sources_sha256` (comments
+and blank lines do not count)."""
 import collections
 import csv
 import hashlib
@@ -38,6 +39,19 @@ from sass_static_table import function_ranges  # noqa: E402
 SOURCES = ["bh8_ray.cuh", "bh8_kernel.cuh", "bh8_warp.cuh", "bh8_frame.h"]
 TAG = "bh8_render_kernelILi1ELb0ELi2E"
 FLOPS = {"DFMA": 2, "DMUL": 1, "DADD": 1}
+
+
+def sources_digest(src_dir, names):
+    """sha256 of the kernel sources as the compiler sees them: comments, blank lines and indentation removed, so
+    that rewording a comment does not orphan the model (bench.py carries the same function)."""
+    h = hashlib.sha256()
+    for n in names:
+        with open(os.path.join(src_dir, n)) as f:
+            text = f.read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        h.update("\n".join(ln.strip() for ln in text.splitlines() if ln.strip()).encode())
+    return h.hexdigest()
 
 
 def chains(so):
@@ -140,15 +154,11 @@ def main():
     cycles = metric("sm__cycles_elapsed.avg") or metric("smsp__cycles_elapsed.avg")
     if all(n in col for n in names) and cycles:
         thread_flops = (2 * metric(names[0]) + metric(names[1]) + metric(names[2])) * cycles
-    h = hashlib.sha256()
-    for n in SOURCES:
-        with open(os.path.join(src, n), "rb") as f:
-            h.update(f.read())
     git = subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip()
     fixed = per.get("setup", 0) + per.get("rare", 0) + per.get("other", 0)
     model = {
         "what": "instruction model of bh8_render_kernel<1,false,2> (tools/instr_model.py), calibrated on configs[1] 1920x1080",
-        "git": git, "sources": SOURCES, "sources_sha256": h.hexdigest(),
+        "git": git, "sources": SOURCES, "sources_sha256": sources_digest(src, SOURCES),
         "captured": {"warps": warps, "update_slots_per_warp": slots, "resolve_passes_per_warp": passes,
                      "instr_per_warp_by_phase": per, "fp64_flops_per_lane_per_warp_by_phase": fl,
                      "instr_per_warp": sum(per.values())},
