@@ -155,10 +155,13 @@ int launch_built(bh8_ctx* ctx, Device& d, Bh8Frame& f, void* d_pixels, void* d_c
   const unsigned tiles = grid.x * grid.y, wave = static_cast<unsigned>(d.sm_count) * BH8_MIN_BLOCKS;
   grid = dim3(tiles < wave ? tiles : wave, 1, 1);
 #endif
+#ifndef BH8_FINE_UPV
+#define BH8_FINE_UPV 3  // updates per round of votes at fine steps (A/B knob)
+#endif
 #define BH8_LAUNCH2(NN_, ST_)                                                              \
   do {                                                                                     \
     if (f.nstep >= bh8::kFineNstep)                                                        \
-      bh8::bh8_render_kernel<NN_, ST_, 3><<<grid, bh8::kThreads, ctx->extra_smem, st>>>(f, tex, out);    \
+      bh8::bh8_render_kernel<NN_, ST_, BH8_FINE_UPV><<<grid, bh8::kThreads, ctx->extra_smem, st>>>(f, tex, out);    \
     else                                                                                   \
       bh8::bh8_render_kernel<NN_, ST_, 2><<<grid, bh8::kThreads, ctx->extra_smem, st>>>(f, tex, out);    \
   } while (0)
