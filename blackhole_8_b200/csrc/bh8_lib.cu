@@ -316,8 +316,10 @@ int bh8_create(bh8_ctx** out, const int* devices, int n_dev) {
     }
     BH8_CREATE_CUDA(cudaEventCreate(&d.ev_t0));
     BH8_CREATE_CUDA(cudaEventCreate(&d.ev_t1));
-    // Frames are gathered on device 0: the other devices store into its memory over NVLink.
-    if (i > 0) {
+    // Frames are gathered on device 0: the other devices store into its memory over NVLink.  An ordinal
+    // listed twice is a second logical device on the same GPU (own streams, buffers and textures; the
+    // gather is then an ordinary store): the sharding logic can be exercised on a one-GPU box.
+    if (i > 0 && d.ordinal != ctx->dev[0].ordinal) {
       int can = 0;
       BH8_CREATE_CUDA(cudaDeviceCanAccessPeer(&can, d.ordinal, ctx->dev[0].ordinal));
       if (!can) {

@@ -155,7 +155,8 @@ typedef struct bh8_stats {
 typedef struct bh8_ctx bh8_ctx;
 
 /* Create a context driving n_dev CUDA devices (devices[i] = ordinal; NULL = {0..n_dev-1}).
- * With n_dev > 1 peer access to devices[0] is enabled and frames are gathered there. */
+ * With n_dev > 1 peer access to devices[0] is enabled and frames are gathered there.  An ordinal may be
+ * listed more than once: each entry is a logical device of its own (streams, buffers, textures). */
 int bh8_create(bh8_ctx** out, const int* devices, int n_dev);
 /* Sinks and scripts opened on the context use its device, streams and textures: close them first. */
 void bh8_destroy(bh8_ctx* ctx);

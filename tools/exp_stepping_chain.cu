@@ -89,6 +89,35 @@ __global__ void __launch_bounds__(256, 5) probe_pair(double* sink, int updates, 
   }
   if (phi == 123.456 || parked == updates + 1) sink[0] = phi + parked;
 }
+
+// Operand-mix variants of the update (tools/exp_fp64_operands.cu: a DFMA whose three sources are all fresh registers
+// costs more than 2 SMSP-cycles).  FORM bit 0: the rsqrt correction as y * (1 + e p) -- DFMA(reg, reg, imm) + DMUL --
+// instead of DFMA(y e, p, y); bit 1: the angle kept as the plain sum of s (DADD), multiplied by du/2 on demand.
+template <int FORM>
+__global__ void __launch_bounds__(256, 5) probe_form(double* sink, int updates, double two_m_, double u0, double du, double binv2_0) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const double delta = du * (1.0 + 1e-4 * (gid & 1023)), du_h = 0.5 * delta;
+  const double binv2 = binv2_0 * (1.0 + 1e-3 * (gid & 255));
+  double two_m = two_m_, k375 = 0.375;
+  asm volatile("" : "+d"(two_m), "+d"(k375));
+  const uint32_t t_thr = 0x7ff00000u, trig_hi = 0x7ff00000u;
+  double ud = u0, phid = 0.0, prev = 0.0; int parked = 0;
+  for (int i = 0; i < updates; ++i) {
+    ud += delta;
+    const double x = fma(ud * ud, fma(two_m, ud, -1.0), binv2);
+    const double y = seed<0>(x);
+    const double e = fma(-(x * y), y, 1.0);
+    double dphi;
+    if (FORM & 1) dphi = y * fma(e, fma(e, k375, 0.5), 1.0);
+    else dphi = fma(y * e, fma(e, k375, 0.5), y);
+    const double s = prev + dphi;
+    prev = dphi;
+    if (FORM & 2) phid += s;
+    else phid = fma(s, du_h, phid);
+    if (hi_word(s) >= t_thr || hi_word(phid) >= trig_hi) ++parked;
+  }
+  if (phid * du_h == 123.456 || parked == updates + 1) sink[0] = phid + parked;
+}
 template <typename K> void run_k(const char* name, K kern) {
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
   double* sink; cudaMalloc(&sink, 8);
@@ -130,5 +159,9 @@ int main() {
   run<3>("no seed (refinement only)");
   run_k("two rays per thread (ILP 2)", probe2);
   run_k("two consecutive updates", probe_pair);
+  run_k("form 0 (shipped, as template)", probe_form<0>);
+  run_k("form 1: y*(1+e p)", probe_form<1>);
+  run_k("form 2: angle as plain sum", probe_form<2>);
+  run_k("form 3: both", probe_form<3>);
   return 0;
 }
