@@ -577,19 +577,29 @@ def instruction_model():
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_instr_model.json")))
     if not files:
         return None
-    with open(files[-1]) as f:
-        model = json.load(f)
     import re
-    h = hashlib.sha256()  # the sources as the compiler sees them: no comments, no blank lines (tools/instr_model.py)
     src = os.path.join(ROOT, "blackhole_8_b200", "csrc")
-    for n in model.get("sources", []):
-        with open(os.path.join(src, n)) as f:
-            text = f.read()
-        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-        text = re.sub(r"//[^\n]*", "", text)
-        h.update("\n".join(ln.strip() for ln in text.splitlines() if ln.strip()).encode())
-    model["file"] = os.path.relpath(files[-1], ROOT)
-    model["matches_running_sources"] = h.hexdigest() == model.get("sources_sha256")
+
+    def digest(names):  # the sources as the compiler sees them: no comments, no blank lines (tools/instr_model.py)
+        h = hashlib.sha256()
+        for n in names:
+            with open(os.path.join(src, n)) as f:
+                text = f.read()
+            text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+            text = re.sub(r"//[^\n]*", "", text)
+            h.update("\n".join(ln.strip() for ln in text.splitlines() if ln.strip()).encode())
+        return h.hexdigest()
+
+    model = None
+    for path in reversed(files):  # the newest model made from the running sources, else the newest (marked stale)
+        with open(path) as f:
+            m = json.load(f)
+        m["file"] = os.path.relpath(path, ROOT)
+        m["matches_running_sources"] = digest(m.get("sources", [])) == m.get("sources_sha256")
+        if model is None or m["matches_running_sources"]:
+            model = m
+        if m["matches_running_sources"]:
+            break
     return model
 
 
@@ -929,8 +939,10 @@ def main():
                 "achieved_what": "FP64 flops the kernel EXECUTES per launch (17 per lane-update x 32 lanes x update slots, "
                                  "counted by the device; + the static per-ray / per-pass FP64 count of the instruction "
                                  "model when it matches the sources) / kernel time: <= peak by construction",
-                "peak_source": "DFMA chain measured in this run (bh8_measure_fp64_peak); MEASURED_PEAKS.json has "
-                               "no FP64 vector figure",
+                "peak_source": "DFMA chain measured in this run (bh8_measure_fp64_peak: two register sources + an "
+                               "immediate, the pipe's own rate -- a DFMA with three register sources is bound by "
+                               "operand reads, profiles/r02_fp64_operand_mix.txt); MEASURED_PEAKS.json has no FP64 "
+                               "vector figure",
                 "hw": hw,
                 "algorithmic": {"flops_per_launch": flops_alg, "TFLOPs": flops_alg / sec / 1e12,
                                 "over_peak": flops_alg / sec / peak,

@@ -516,21 +516,24 @@ bh8_stepping_probe_kernel(double* sink, int updates, double two_m, double u0, do
   if (phi == (Real)123.456 || parked == updates + 1) sink[0] = (double)phi + parked;
 }
 
-// FP64 pipe peak: 8 independent DFMA chains per thread, enough warps to fill every SM.
+// FP64 pipe peak: 8 independent DFMA chains per thread, enough warps to fill every SM.  The addend is an
+// immediate: a DFMA whose three sources are all registers is bound by operand reads, not by the pipe, on B200
+// (2.18 SMSP-cycles per warp instruction with the reuse cache, 3.0 with three fresh registers, 2.01 with two:
+// tools/exp_fp64_operands.cu, profiles/r02_fp64_operand_mix.txt) -- the yardstick must not be.
 __global__ void __launch_bounds__(256, 4) bh8_dfma_peak_kernel(double* sink, int iters, double a, double b) {
-  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+  double x0 = threadIdx.x * 1e-9 + b, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
          x7 = x0 + 7;
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      x0 = fma(x0, a, b);
-      x1 = fma(x1, a, b);
-      x2 = fma(x2, a, b);
-      x3 = fma(x3, a, b);
-      x4 = fma(x4, a, b);
-      x5 = fma(x5, a, b);
-      x6 = fma(x6, a, b);
-      x7 = fma(x7, a, b);
+      x0 = fma(x0, a, 0.5);
+      x1 = fma(x1, a, 0.5);
+      x2 = fma(x2, a, 0.5);
+      x3 = fma(x3, a, 0.5);
+      x4 = fma(x4, a, 0.5);
+      x5 = fma(x5, a, 0.5);
+      x6 = fma(x6, a, 0.5);
+      x7 = fma(x7, a, 0.5);
     }
   }
   const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
