@@ -48,6 +48,10 @@ struct Device {
   cudaEvent_t ev_kernel_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_copy_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  // bh8_render of ONE frame on one device: the frame is drawn as kMaxBands row bands, band k read back
+  // while band k+1 is drawn
+  static constexpr int kMaxBands = 8;
+  cudaEvent_t ev_band[kMaxBands] = {};
   bool timing_open = false;
   bool slot_busy[2] = {false, false};  // bh8_submit: a frame whose read-back has not been waited for
 };
@@ -63,6 +67,9 @@ struct bh8_ctx {
   uint64_t launches = 0;
   uint64_t next_ticket = 0;  // bh8_submit
   bool submit_slot_streams = true;  // $BH8_SUBMIT_ONE_STREAM=1: kernels on one stream, copies on another (A/B knob)
+  int render_bands = 5;             // $BH8_RENDER_BANDS: row bands of a single-frame bh8_render (1 = whole frame, then the
+                                    // copy); measured best of 1..8 at 1920x1080 (profiles/r02bh_render_bands.txt)
+  bool band_two_streams = true;     // $BH8_RENDER_BANDS_ONE_STREAM=1: all bands on one stream (A/B knob)
   int resolve_wait = 0x7fffffff;    // $BH8_RESOLVE_WAIT: tuning knob for the batching window, read once at creation
   size_t extra_smem = 0;            // $BH8_EXTRA_SMEM: unused dynamic shared memory per CTA (occupancy experiments)
   std::vector<void*> owned;  // bh8_frame_alloc results (device 0)
@@ -274,6 +281,11 @@ int bh8_create(bh8_ctx** out, const int* devices, int n_dev) {
   ctx->n_dev = n_dev;
   if (const char* one = std::getenv("BH8_SUBMIT_ONE_STREAM")) ctx->submit_slot_streams = std::atoi(one) == 0;
   if (const char* w = std::getenv("BH8_RESOLVE_WAIT")) ctx->resolve_wait = std::atoi(w);
+  if (const char* o = std::getenv("BH8_RENDER_BANDS_ONE_STREAM")) ctx->band_two_streams = std::atoi(o) == 0;
+  if (const char* nb = std::getenv("BH8_RENDER_BANDS")) {
+    const int v = std::atoi(nb);
+    ctx->render_bands = v < 1 ? 1 : (v > Device::kMaxBands ? Device::kMaxBands : v);
+  }
   if (const char* x = std::getenv("BH8_EXTRA_SMEM")) ctx->extra_smem = static_cast<size_t>(std::atoi(x));
   for (int i = 0; i < n_dev; ++i) {
     Device& d = ctx->dev[i];
@@ -314,6 +326,8 @@ int bh8_create(bh8_ctx** out, const int* devices, int n_dev) {
       BH8_CREATE_CUDA(cudaEventCreateWithFlags(&d.ev_kernel_done[b], cudaEventDisableTiming));
       BH8_CREATE_CUDA(cudaEventCreateWithFlags(&d.ev_copy_done[b], cudaEventDisableTiming));
     }
+    for (int b = 0; b < Device::kMaxBands; ++b)
+      BH8_CREATE_CUDA(cudaEventCreateWithFlags(&d.ev_band[b], cudaEventDisableTiming));
     BH8_CREATE_CUDA(cudaEventCreate(&d.ev_t0));
     BH8_CREATE_CUDA(cudaEventCreate(&d.ev_t1));
     // Frames are gathered on device 0: the other devices store into its memory over NVLink.  An ordinal
@@ -354,6 +368,8 @@ void bh8_destroy(bh8_ctx* ctx) {
       if (d.ev_kernel_done[b]) cudaEventDestroy(d.ev_kernel_done[b]);
       if (d.ev_copy_done[b]) cudaEventDestroy(d.ev_copy_done[b]);
     }
+    for (int b = 0; b < Device::kMaxBands; ++b)
+      if (d.ev_band[b]) cudaEventDestroy(d.ev_band[b]);
     if (d.ev_t0) cudaEventDestroy(d.ev_t0);
     if (d.ev_t1) cudaEventDestroy(d.ev_t1);
     cudaFree(d.d_stats);
@@ -564,6 +580,54 @@ int render_batch(bh8_ctx* ctx, const bh8_scene* scenes, const bh8_camera* cams, 
                                       d0.copy_stream));
       BH8_CUDA(ctx, cudaEventRecord(d0.ev_copy_done[b], d0.copy_stream));
     }
+  } else if (n_frames == 1 && ctx->render_bands > 1 && cams[0].height >= 64 * ctx->render_bands) {
+    // ONE frame, one device: nothing of the next frame to draw under this one's read-back, so the frame
+    // itself is cut into row bands (the stripe mapping with one stripe per band): all bands are launched
+    // back to back, band k leaves for the host while band k+1 is drawn, and the call ends one band's copy
+    // after the last kernel instead of one frame's.
+    Device& d = ctx->dev[0];
+    BH8_CUDA(ctx, cudaSetDevice(d.ordinal));
+    const int W = cams[0].width, H = cams[0].height, nb = ctx->render_bands;
+    const int band_rows = (((H + nb - 1) / nb) + bh8::kTileH - 1) / bh8::kTileH * bh8::kTileH;
+    bh8_params p = prm;
+    p.stripe_rows = band_rows;
+    p.shard_count = nb;
+    p.shard_index = 0;
+    Bh8Frame f;  // the frame constants are built once; a band differs in its shard index only
+    char msg[192];
+    const int rcb = bh8_build_frame(&scenes[0], &cams[0], &p, ctx->tex_rows, ctx->tex_cols, &f, msg);
+    if (rcb != BH8_OK) return fail(ctx, rcb, msg);
+    if (ctx->resolve_wait != 0x7fffffff) f.resolve_wait = ctx->resolve_wait;
+    if (p.flags & BH8_FLAG_NO_BATCHING) f.resolve_wait = -1;
+    // Bands alternate between two streams, so that band k+1 starts on the SMs band k's last wave leaves idle
+    // (as bh8_submit does with whole frames); the second stream starts after ev_t0 and joins before ev_t1.
+    cudaStream_t lane[2] = {d.stream, ctx->band_two_streams ? d.slot_stream[0] : d.stream};
+    if (lane[1] != lane[0]) BH8_CUDA(ctx, cudaStreamWaitEvent(lane[1], d.ev_t0, 0));
+    for (int k = 0; k < nb; ++k) {
+      f.shard_index = k;
+      const int rc = launch_built(ctx, d, f, d.d_pix[0], out_class ? d.d_cls[0] : nullptr,
+                                  out_key ? d.d_key[0] : nullptr, out_steps ? d.d_steps[0] : nullptr, lane[k & 1]);
+      if (rc != BH8_OK) return rc;
+      BH8_CUDA(ctx, cudaEventRecord(d.ev_band[k], lane[k & 1]));
+    }
+    if (lane[1] != lane[0])
+      for (int k = 1; k < nb; k += 2) BH8_CUDA(ctx, cudaStreamWaitEvent(d.stream, d.ev_band[k], 0));
+    for (int k = 0; k < nb; ++k) {
+      const int y0 = k * band_rows, y1 = y0 + band_rows < H ? y0 + band_rows : H;
+      if (y0 >= H) break;
+      const size_t off = static_cast<size_t>(y0) * W, n = static_cast<size_t>(y1 - y0) * W;
+      BH8_CUDA(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_band[k], 0));
+      BH8_CUDA(ctx, cudaMemcpyAsync(out_pixels + off * bpp, static_cast<uint8_t*>(d.d_pix[0]) + off * bpp, n * bpp,
+                                    cudaMemcpyDeviceToHost, d.copy_stream));
+      if (out_class)
+        BH8_CUDA(ctx, cudaMemcpyAsync(out_class + off, d.d_cls[0] + off, n, cudaMemcpyDeviceToHost, d.copy_stream));
+      if (out_key)
+        BH8_CUDA(ctx, cudaMemcpyAsync(out_key + off, d.d_key[0] + off, n, cudaMemcpyDeviceToHost, d.copy_stream));
+      if (out_steps)
+        BH8_CUDA(ctx, cudaMemcpyAsync(out_steps + off, d.d_steps[0] + off, n * 2, cudaMemcpyDeviceToHost,
+                                      d.copy_stream));
+    }
+    BH8_CUDA(ctx, cudaEventRecord(d.ev_copy_done[0], d.copy_stream));
   } else {
     // whole frames dealt round-robin; per device: kernel(f) -> D2H(f) overlaps kernel(f+1)
     std::vector<int> issued(ctx->n_dev, 0);

@@ -172,7 +172,9 @@ int bh8_set_texture(bh8_ctx* ctx, int tex_id, const uint8_t* bgr, int rows, int 
  * buffers of n_frames * H * W bytes (hit class; ObjectManager key of the hit object, -1 = none);
  * out_steps (nullable): n_frames * H * W uint16 step counts.  Synchronous; includes the
  * host<->device copies.  With several devices whole frames are dealt round-robin when
- * n_frames >= n_dev, else each frame is striped over the devices (params->stripe_rows, default 16). */
+ * n_frames >= n_dev, else each frame is striped over the devices (params->stripe_rows, default 16).
+ * One frame on one device is drawn as five row bands (BH8_RENDER_BANDS, 1..8), each read back while the
+ * next is drawn: the call ends one band's copy after the last kernel, not one frame's. */
 int bh8_render(bh8_ctx* ctx, const bh8_scene* scenes, const bh8_camera* cams, int n_frames,
                const bh8_params* params, uint8_t* out_pixels, uint8_t* out_class, int8_t* out_key,
                uint16_t* out_steps, bh8_stats* stats);

@@ -189,3 +189,29 @@ def test_streaming_submit_wait_equals_render(G):
     assert np.array_equal(bufs[prev[1]].array, want[prev[1]])
     for b in bufs:
         b.free()
+
+
+def test_single_frame_render_in_row_bands_equals_whole_frame(monkeypatch):
+    """bh8_render of ONE frame draws it as row bands (band k is read back while band k+1 is drawn, bands on two
+    streams); pixels, maps and counters must equal the unbanded call's ($BH8_RENDER_BANDS=1), also when the
+    height is not a multiple of the band height."""
+    from blackhole_8_b200.renderer import Renderer
+    results = {}
+    for bands in ("1", "3", "4", "5"):
+        monkeypatch.setenv("BH8_RENDER_BANDS", bands)
+        r = Renderer((0,))
+        try:
+            for name in ("cfg1_640x360", "cfg2_640x360"):
+                snap = O.load_golden(name)["snap"]
+                r.set_textures(snap, O.load_texture)
+                for fmt in (abi.PIXEL_BGR8, abi.PIXEL_RGBA8):
+                    res = r.render(snap, pixel_format=fmt, want_maps=True, stats=True)
+                    results[(bands, name, fmt)] = ({k: np.array(res[k]) for k in ("pixels", "cls", "key", "steps")},
+                                                   (res["stats"].rays, res["stats"].steps))
+        finally:
+            r.close()
+    for (bands, name, fmt), (maps, counts) in results.items():
+        want_maps, want_counts = results[("1", name, fmt)]
+        for k in maps:
+            assert np.array_equal(maps[k], want_maps[k]), (bands, name, fmt, k)
+        assert counts == want_counts, (bands, name, fmt)
