@@ -812,6 +812,24 @@ int bh8_host_alloc_flags(void** p, size_t bytes, unsigned flags) {
   return cudaHostAlloc(p, bytes, f) == cudaSuccess ? BH8_OK : BH8_ENOMEM;
 }
 
+int bh8_host_register(void* p, size_t bytes) {
+  if (!p || bytes == 0) return BH8_EINVAL;
+  const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (e == cudaSuccess || e == cudaErrorHostMemoryAlreadyRegistered) {
+    (void)cudaGetLastError();
+    return BH8_OK;
+  }
+  (void)cudaGetLastError();
+  return e == cudaErrorMemoryAllocation ? BH8_ENOMEM : BH8_ECUDA;
+}
+
+int bh8_host_unregister(void* p) {
+  if (!p) return BH8_EINVAL;
+  const cudaError_t e = cudaHostUnregister(p);
+  (void)cudaGetLastError();
+  return e == cudaSuccess ? BH8_OK : BH8_ECUDA;
+}
+
 int bh8_measure_d2h(bh8_ctx* ctx, uint8_t* host_a, uint8_t* host_b, size_t bytes, int reps, double* seconds) {
   if (!ctx || !host_a || !host_b || bytes == 0 || reps < 1 || !seconds) return BH8_EINVAL;
   Device& d = ctx->dev[0];

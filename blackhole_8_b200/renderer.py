@@ -64,6 +64,8 @@ def load_library(path=None):
         "bh8_host_alloc_flags": (i32, [C.POINTER(vp), C.c_size_t, C.c_uint]),
         "bh8_measure_d2h": (i32, [vp, vp, vp, C.c_size_t, i32, C.POINTER(C.c_double)]),
         "bh8_host_free": (i32, [vp]),
+        "bh8_host_register": (i32, [vp, C.c_size_t]),
+        "bh8_host_unregister": (i32, [vp]),
         "bh8_measure_fp64_peak": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "bh8_measure_stepping": (i32, [vp, i32, C.POINTER(C.c_double)]),
         "bh8_script_create": (i32, [vp, C.POINTER(abi.Scene), C.POINTER(abi.Basis), C.POINTER(abi.Camera),
@@ -277,6 +279,14 @@ class Renderer:
 
     def pinned(self, shape, dtype=np.uint8, write_combined=False):
         return PinnedBuffer(self.lib, shape, dtype, write_combined)
+
+    def host_register(self, array):
+        """Pin a numpy array the caller owns (bh8_host_register): read-backs into it become plain DMA.  Costs
+        ~19 ms; call host_unregister(array) before the array is freed."""
+        self._check(self.lib.bh8_host_register(array.ctypes.data_as(C.c_void_p), array.nbytes))
+
+    def host_unregister(self, array):
+        self._check(self.lib.bh8_host_unregister(array.ctypes.data_as(C.c_void_p)))
 
     def measure_d2h(self, buf_a, buf_b, nbytes, reps):
         """Seconds for `reps` read-backs of nbytes each into the two pinned buffers, no kernels (bh8_measure_d2h)."""

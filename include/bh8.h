@@ -221,6 +221,12 @@ int bh8_host_alloc(void** p, size_t bytes);
 #define BH8_HOST_WRITE_COMBINED 1u /* cudaHostAllocWriteCombined: faster DMA target, slow for the CPU to read */
 int bh8_host_alloc_flags(void** p, size_t bytes, unsigned flags);
 int bh8_host_free(void* p);
+/* Pin memory the caller already owns (cudaHostRegister, portable) -- e.g. the cv::Mat frame a driver hands to
+ * bh8_render() every frame: a read-back into pageable memory is staged by the driver and takes 0.58 ms per
+ * 1080p BGR8 frame instead of 0.21 (profiles/r02bj_pageable.txt).  Registering costs ~19 ms once; unregister
+ * before the memory is freed. */
+int bh8_host_register(void* p, size_t bytes);
+int bh8_host_unregister(void* p);
 /* Read-back ceiling of this process' GPU: `reps` device-to-host copies of `bytes` each, alternating
  * between the two pinned buffers exactly as bh8_submit() queues its frames' read-backs (staging slot ->
  * host, one copy per slot in flight) but with no kernel in between; wall time in *seconds. */

@@ -27,9 +27,25 @@ class Renderer {
     if (bh8_create(&ctx_, devices.data(), static_cast<int>(devices.size())) != BH8_OK)
       throw std::runtime_error(std::string("bh8_create: ") + bh8_last_error(nullptr));
   }
-  ~Renderer() { bh8_destroy(ctx_); }
+  ~Renderer() {
+    bh8_destroy(ctx_);
+    for (void* p : pinned_) bh8_host_free(p);
+  }
   Renderer(const Renderer&) = delete;
   Renderer& operator=(const Renderer&) = delete;
+
+  // An H x W CV_8UC3 frame in PINNED host memory owned by this Renderer (valid until it is destroyed): the
+  // read-back into it is a plain DMA.  A frame in pageable memory -- any cv::Mat the caller allocated -- is
+  // staged by the driver: 0.58 instead of 0.21 ms per 1080p frame (profiles/r02bj_pageable.txt).  Render()
+  // hands out such frames itself whenever it has to allocate the frame (an empty Mat, another size); a Mat
+  // the caller keeps allocating afresh stays pageable after kMaxPinnedFrames of them.
+  cv::Mat PinnedFrame(int rows, int cols) {
+    void* p = nullptr;
+    if (bh8_host_alloc(&p, static_cast<size_t>(rows) * cols * 3) != BH8_OK)
+      throw std::runtime_error("bh8_host_alloc: out of pinned host memory");
+    pinned_.push_back(p);
+    return cv::Mat(rows, cols, CV_8UC3, p);
+  }
 
   bh8_ctx* context() { return ctx_; }
   const bh8_stats& last_stats() const { return stats_; }
@@ -98,10 +114,12 @@ class Renderer {
 
   // The frame the kernels' rows are copied into: H x W CV_8UC3 with rows back to back (a ROI or padded Mat is
   // replaced by a fresh one rather than written through with the wrong stride).
-  static void EnsureFrame(const bh8_camera& cam, cv::Mat* frame) {
+  static constexpr size_t kMaxPinnedFrames = 8;
+  void EnsureFrame(const bh8_camera& cam, cv::Mat* frame) {
     if (frame->empty() || frame->rows != cam.height || frame->cols != cam.width || frame->type() != CV_8UC3 ||
         !frame->isContinuous())
-      *frame = cv::Mat(cam.height, cam.width, CV_8UC3);
+      *frame = pinned_.size() < kMaxPinnedFrames ? PinnedFrame(cam.height, cam.width)
+                                                 : cv::Mat(cam.height, cam.width, CV_8UC3);
   }
 
   // Textures are re-sent when a slot's image changes: another buffer, another size or row stride.  (A caller
@@ -130,6 +148,7 @@ class Renderer {
   bh8_ctx* ctx_ = nullptr;
   bh8_stats stats_{};
   std::vector<TexKey> uploaded_;
+  std::vector<void*> pinned_;  // PinnedFrame() buffers, freed with the Renderer
   friend class VideoWriter;
   friend class Script;
 };
@@ -228,8 +247,10 @@ class Script {
   // Frame `frame` into a CV_8UC3 (BGR) cv::Mat, like Renderer::Render.
   void Render(int frame, cv::Mat* out) {
     if (!script_) throw std::runtime_error("Script::Render before Compile");
-    if (out->empty() || out->rows != height_ || out->cols != width_ || out->type() != CV_8UC3)
-      *out = cv::Mat(height_, width_, CV_8UC3);
+    bh8_camera shape{};
+    shape.width = width_;
+    shape.height = height_;
+    gpu_->EnsureFrame(shape, out);  // a pinned frame of the Renderer's when it has to be allocated
     gpu_->Check(bh8_script_render(script_, frame, d_frame_, nullptr, nullptr, nullptr));
     gpu_->Check(bh8_memcpy_d2h(gpu_->ctx_, out->data, d_frame_, static_cast<size_t>(width_) * height_ * 3));
   }
