@@ -5,6 +5,7 @@
 // tests/host_harness/_build/; the product library never contains or calls it -- there is no CPU
 // rendering path in libbh8.so.
 #include <cstdint>
+#include <cstdio>
 #include <cmath>
 #include <cstring>
 
@@ -137,6 +138,65 @@ extern "C" int bh8_harness_render(const bh8_scene* scene, const bh8_camera* cam,
     case 4: trace_frame<4>(f, fetch, out_bgr, out_class, out_key, out_steps, counters); break;
     default: trace_frame<-1>(f, fetch, out_bgr, out_class, out_key, out_steps, counters); break;
   }
+  return BH8_OK;
+}
+
+// Debugging aid: ONE pixel, the lane's registers and the filter-(2) words of its mailbox printed after every
+// update and every exact pass (tests/debug_pixel.py).
+template <int NN>
+static void trace_pixel(const Bh8Frame& f, const HostFetch& fetch, int x, int y) {
+  bh8::Lane<NN> L;
+  double md[bh8::kMailDoubles];
+  int32_t mw[bh8::kMailInts];
+  std::memset(md, 0, sizeof md);
+  std::memset(mw, 0, sizeof mw);
+  const bh8::Mail mail{md, mw, 1};
+  bh8::lane_setup(f, x, y, L, mail);
+  bh8::lane_park_constants(L, mail);
+  std::printf("NN %d n_nc %d nstep %d evt_turn %d u0 %.9g u_gate %.9g lease_ku %.6g lease_kphi %.6g max_n %.6g max_c %.6g\n", NN, f.n_nc,
+              f.nstep, f.evt_turn, f.u0, f.u_gate, (double)f.lease_ku, (double)f.lease_kphi, (double)f.nc_max_n, (double)f.nc_max_c);
+  auto show = [&](const char* what) {
+    std::printf("%-7s idx %3d state %d u %.12g phi %.12g delta %.6g du_h %.6g lo %d span %u trig_hi %08x flags %02x "
+                "gate_in %d gate_out %d next %d fbits %08x fstep %d\n", what, L.idx(), (int)L.state, L.u, L.phi, L.delta, L.du_h,
+                (int)L.lo, (unsigned)L.span, (unsigned)L.trig_hi, (unsigned)mail.get_w(bh8::kMwFlags) & 0xffu,
+                NN != 0 ? mail.get_w(bh8::kMwGateIn) : 0, NN != 0 ? mail.get_w(bh8::kMwGateOut) : 0,
+                mail.get_w(bh8::kMwNext), (unsigned)mail.get_w(bh8::kMwFbits), mail.get_w(bh8::kMwFstep));
+  };
+  show("setup");
+  for (int guard = 0; guard < 100000 && L.state != bh8::kDead; ++guard) {
+    if (L.state == bh8::kRun) {
+      bh8::lane_update(f, L, mail, bh8::StepConst::load(f));
+      show("update");
+    } else {
+      const bool alive = bh8::lane_resolve(f, L, mail, fetch);
+      show("resolve");
+      if (!alive) break;
+    }
+  }
+  std::printf("result: steps %d hit %d\n", bh8::mail_steps(mail), bh8::mail_hit(mail));
+}
+
+extern "C" int bh8_harness_trace_pixel(const bh8_scene* scene, const bh8_camera* cam, const bh8_params* prm,
+                                       const HarnessTexture* textures, int n_textures, int filter_slots, int x, int y,
+                                       char* err) {
+  int rows[BH8_MAX_TEXTURES] = {0}, cols[BH8_MAX_TEXTURES] = {0};
+  for (int i = 0; i < n_textures && i < BH8_MAX_TEXTURES; ++i) {
+    rows[i] = textures[i].rows;
+    cols[i] = textures[i].cols;
+  }
+  Bh8Frame f;
+  const int rc = bh8_build_frame(scene, cam, prm, rows, cols, &f, err);
+  if (rc != BH8_OK) return rc;
+  const HostFetch fetch{textures};
+  switch ((filter_slots >= 0 && f.n_nc <= 4) ? f.n_nc : -1) {
+    case 0: trace_pixel<0>(f, fetch, x, y); break;
+    case 1: trace_pixel<1>(f, fetch, x, y); break;
+    case 2: trace_pixel<2>(f, fetch, x, y); break;
+    case 3: trace_pixel<3>(f, fetch, x, y); break;
+    case 4: trace_pixel<4>(f, fetch, x, y); break;
+    default: trace_pixel<-1>(f, fetch, x, y); break;
+  }
+  std::fflush(stdout);
   return BH8_OK;
 }
 
