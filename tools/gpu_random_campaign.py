@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """One-off parity campaign beyond the test suite's 48 GPU seeds: seeded random scenes (tests/random_scenes.py)
 rendered by the CUDA path through the C ABI and by the C oracle, differences counted per pixel.
-usage (GPU box): python tools/gpu_random_campaign.py [first_seed] [n_scenes] > profiles/rNN_random_campaign.txt"""
+usage (GPU box): python tools/gpu_random_campaign.py [first_seed] [n_scenes] [nstep list, e.g. 64,100,200] > profiles/rNN_random_campaign.txt
+With an nstep list the scenes' own step counts (7 / 20 / 50) are replaced by its entries in turn: from 64 on the kernel
+takes its fine-step instantiation (three updates per round of votes)."""
 import os
 import sys
 import time
@@ -20,6 +22,7 @@ def main():
     from random_scenes import random_snapshot
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    nsteps = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else None
     tot = dict(pixels=0, cls=0, rgb=0, steps=0, scenes_with_any=0)
     classes = np.zeros(4, np.int64)
     worst = []
@@ -27,8 +30,9 @@ def main():
     for seed in range(first, first + n):
         W, H = ((192, 108), (256, 144), (333, 187))[seed % 3]
         snap = random_snapshot(seed, W, H)
-        ref = O.render(snap)
-        got = gpu_render(snap, stats=bool(seed & 1))  # both kernel instantiations
+        ns = nsteps[seed % len(nsteps)] if nsteps else None
+        ref = O.render(snap, nstep=ns)
+        got = gpu_render(snap, nstep=ns, stats=bool(seed & 1))  # both kernel instantiations
         cls_bad = int((got["cls"] != ref["cls"]).sum())
         diff = np.abs(got["bgr"].astype(int) - ref["bgr"].astype(int)).max(axis=2)
         rgb_bad = int(((got["cls"] == ref["cls"]) & (diff > parity.RGB_TOL)).sum())
@@ -41,8 +45,9 @@ def main():
         if cls_bad or rgb_bad or steps_bad:
             tot["scenes_with_any"] += 1
             worst.append((cls_bad + rgb_bad + steps_bad, seed, cls_bad, rgb_bad, steps_bad, W, H))
-    print("random scenes %d..%d (%d scenes, %d pixels, frame sizes 192x108 / 256x144 / 333x187, nstep 7 / 20 / 50), "
-          "CUDA path vs C oracle, %.0f s" % (first, first + n - 1, n, tot["pixels"], time.time() - t0))
+    print("random scenes %d..%d (%d scenes, %d pixels, frame sizes 192x108 / 256x144 / 333x187, nstep %s), "
+          "CUDA path vs C oracle, %.0f s" % (first, first + n - 1, n, tot["pixels"],
+                                            " / ".join(str(v) for v in nsteps) if nsteps else "7 / 20 / 50", time.time() - t0))
     print("pixels by class (background, horizon, disc, object):", classes.tolist())
     print("hit class differs: %d pixels; colour differs by more than %d/255 (same class): %d pixels; "
           "step count differs: %d pixels; scenes with any difference: %d"
