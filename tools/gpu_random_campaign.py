@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """One-off parity campaign beyond the test suite's 48 GPU seeds: seeded random scenes (tests/random_scenes.py)
 rendered by the CUDA path through the C ABI and by the C oracle, differences counted per pixel.
-usage (GPU box): python tools/gpu_random_campaign.py [first_seed] [n_scenes] [nstep list, e.g. 64,100,200] > profiles/rNN_random_campaign.txt
+usage (GPU box): python tools/gpu_random_campaign.py [first_seed] [n_scenes] [nstep list, e.g. 64,100,200 or -] [sizes, e.g. 640x360,1920x1080] > profiles/rNN_random_campaign.txt
 With an nstep list the scenes' own step counts (7 / 20 / 50) are replaced by its entries in turn: from 64 on the kernel
 takes its fine-step instantiation (three updates per round of votes)."""
 import os
@@ -22,13 +22,15 @@ def main():
     from random_scenes import random_snapshot
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-    nsteps = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else None
+    nsteps = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 and sys.argv[3] != "-" else None
+    sizes = [tuple(int(v) for v in t.split("x")) for t in sys.argv[4].split(",")] if len(sys.argv) > 4 else \
+        [(192, 108), (256, 144), (333, 187)]
     tot = dict(pixels=0, cls=0, rgb=0, steps=0, scenes_with_any=0)
     classes = np.zeros(4, np.int64)
     worst = []
     t0 = time.time()
     for seed in range(first, first + n):
-        W, H = ((192, 108), (256, 144), (333, 187))[seed % 3]
+        W, H = sizes[seed % len(sizes)]
         snap = random_snapshot(seed, W, H)
         ns = nsteps[seed % len(nsteps)] if nsteps else None
         ref = O.render(snap, nstep=ns)
@@ -45,8 +47,8 @@ def main():
         if cls_bad or rgb_bad or steps_bad:
             tot["scenes_with_any"] += 1
             worst.append((cls_bad + rgb_bad + steps_bad, seed, cls_bad, rgb_bad, steps_bad, W, H))
-    print("random scenes %d..%d (%d scenes, %d pixels, frame sizes 192x108 / 256x144 / 333x187, nstep %s), "
-          "CUDA path vs C oracle, %.0f s" % (first, first + n - 1, n, tot["pixels"],
+    print("random scenes %d..%d (%d scenes, %d pixels, frame sizes %s, nstep %s), "
+          "CUDA path vs C oracle, %.0f s" % (first, first + n - 1, n, tot["pixels"], " / ".join("%dx%d" % t for t in sizes),
                                             " / ".join(str(v) for v in nsteps) if nsteps else "7 / 20 / 50", time.time() - t0))
     print("pixels by class (background, horizon, disc, object):", classes.tolist())
     print("hit class differs: %d pixels; colour differs by more than %d/255 (same class): %d pixels; "
