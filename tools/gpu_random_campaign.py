@@ -20,6 +20,12 @@ def main():
     import parity
     from gpu_util import gpu_render
     from random_scenes import random_snapshot
+    # $BH8_CAMPAIGN_DEVICES=0,0,0: through a multi-device context (an ordinal listed twice is a logical device), i.e.
+    # every frame in interleaved 16-row stripes gathered in device 0's buffer
+    r = None
+    if os.environ.get("BH8_CAMPAIGN_DEVICES"):
+        from blackhole_8_b200.renderer import Renderer
+        r = Renderer(tuple(int(v) for v in os.environ["BH8_CAMPAIGN_DEVICES"].split(",")))
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
     nsteps = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 and sys.argv[3] != "-" else None
@@ -34,7 +40,7 @@ def main():
         snap = random_snapshot(seed, W, H)
         ns = nsteps[seed % len(nsteps)] if nsteps else None
         ref = O.render(snap, nstep=ns)
-        got = gpu_render(snap, nstep=ns, stats=bool(seed & 1))  # both kernel instantiations
+        got = gpu_render(snap, nstep=ns, stats=bool(seed & 1), r=r)  # both kernel instantiations
         cls_bad = int((got["cls"] != ref["cls"]).sum())
         diff = np.abs(got["bgr"].astype(int) - ref["bgr"].astype(int)).max(axis=2)
         rgb_bad = int(((got["cls"] == ref["cls"]) & (diff > parity.RGB_TOL)).sum())
@@ -48,8 +54,10 @@ def main():
             tot["scenes_with_any"] += 1
             worst.append((cls_bad + rgb_bad + steps_bad, seed, cls_bad, rgb_bad, steps_bad, W, H))
     print("random scenes %d..%d (%d scenes, %d pixels, frame sizes %s, nstep %s), "
-          "CUDA path vs C oracle, %.0f s" % (first, first + n - 1, n, tot["pixels"], " / ".join("%dx%d" % t for t in sizes),
-                                            " / ".join(str(v) for v in nsteps) if nsteps else "7 / 20 / 50", time.time() - t0))
+          "CUDA path%s vs C oracle, %.0f s" % (first, first + n - 1, n, tot["pixels"], " / ".join("%dx%d" % t for t in sizes),
+                                            " / ".join(str(v) for v in nsteps) if nsteps else "7 / 20 / 50",
+                                            " (devices %s, striped)" % os.environ["BH8_CAMPAIGN_DEVICES"] if r else "",
+                                            time.time() - t0))
     print("pixels by class (background, horizon, disc, object):", classes.tolist())
     print("hit class differs: %d pixels; colour differs by more than %d/255 (same class): %d pixels; "
           "step count differs: %d pixels; scenes with any difference: %d"
