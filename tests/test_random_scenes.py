@@ -10,7 +10,7 @@ import parity
 from random_scenes import random_snapshot
 
 SEEDS = list(range(100))
-GPU_SEEDS = SEEDS[:48]
+GPU_SEEDS = SEEDS[:48] + list(range(100, 250))  # (the campaign of tools/gpu_random_campaign.py goes far beyond)
 
 
 def check(got, ref, what):
