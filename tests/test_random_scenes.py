@@ -100,6 +100,25 @@ def test_gpu_ray_frozen_after_a_start_lease_keeps_its_base_range(seed, width, he
         assert int((got["steps"] != ref["steps"]).sum()) <= 1, stats
 
 
+def test_cpu_campaign_of_random_scenes_at_mixed_sizes():
+    """600 more scenes at five frame sizes through the host-compiled kernel code (every fourth one through the
+    emulated warp schedule too) -- tools/cpu_random_campaign.py in small.  Before the fix above this stretch of
+    seeds held five failing scenes (237, 247, 287 at 160x90; 495 and 500 at 96x54): the campaign needs no GPU
+    to find such a bug."""
+    from test_ray_math_host import harness_render, harness_render_warps
+    bad = []
+    for seed in range(100, 700):
+        w, h = ((96, 54), (128, 72), (160, 90), (192, 108), (64, 36))[seed % 5]
+        snap = random_snapshot(seed, w, h)
+        ref = O.render(snap)
+        got = [harness_render(snap)] + ([harness_render_warps(snap)] if seed % 4 == 0 else [])
+        for g in got:
+            d = int((g["cls"] != ref["cls"]).sum()) + int((g["steps"] != ref["steps"]).sum())
+            if d:
+                bad.append((seed, w, h, d))
+    assert not bad, bad
+
+
 def test_damaged_snapshots_never_hang_the_ray_code():
     """NaN, infinities, zeros and huge values anywhere in a snapshot: the per-ray state machine (the code the
     kernel's lanes run) must still terminate for every pixel -- on the GPU a lane that never ends would hang
